@@ -1,0 +1,1394 @@
+// Host engine + C ABI of libsblx.so.  One handle = one grid model resident on one B200.
+// See include/sblx.h for the reference interfaces each entry point replaces and kernels.cuh for
+// the device side.
+#include "../../include/sblx.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+#include "symbolic.h"
+
+namespace sblx {
+
+static thread_local std::string g_create_error;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) {                                                                                  \
+      char buf_[512];                                                                                         \
+      snprintf(buf_, sizeof buf_, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      throw CudaError(buf_);                                                                                  \
+    }                                                                                                         \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s = 0) {
+    alloc(v.size());
+    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------
+// host model (no CUDA): pattern, maps, symbolic analysis
+// ------------------------------------------------------------------------------------------
+struct HostModel {
+  int n = 0, m = 0, slack = 0, nbr = 0;
+  std::vector<int> y_rowptr, y_col;
+  std::vector<double2> y_val;
+  std::vector<int> node_of_bus, bus_of_node;
+  std::vector<int64_t> jb_rowptr;
+  std::vector<int> jb_row, jb_col, jb_ypos;
+  Symbolic sym;
+  // per bus
+  std::vector<double2> S0, V0;
+  std::vector<double> vset, qmin, qmax, qload;
+  std::vector<unsigned char> type0, lockmask;
+  // branches (0-based buses)
+  std::vector<int> br_from, br_to;
+  std::vector<double2> y11, y12, y21, y22;
+  std::vector<double> rating;
+  std::vector<unsigned char> br_status;
+  // topology helpers
+  std::vector<int> adj_ptr, adj_nb, adj_br;   // in-service branch adjacency
+  std::vector<int> deg;
+  std::vector<int> base_iso;   // buses without any in-service branch in the intact grid
+  int base_islands = 1;
+};
+
+static void build_pattern(HostModel& H, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                          int base, const int32_t* brf, const int32_t* brt, int64_t nbr) {
+  // union pattern: Ybus entries, their transposes, the diagonal and every branch's four stamps
+  std::vector<std::vector<int>> rows(n);
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t p = colptr[j] - base; p < colptr[j + 1] - base; ++p) {
+      int64_t i = rowval[p] - base;
+      if (i < 0 || i >= n) throw std::invalid_argument("sblx_create: Ybus row index out of range");
+      rows[i].push_back((int)j);
+      rows[j].push_back((int)i);
+    }
+  for (int64_t i = 0; i < n; ++i) rows[i].push_back((int)i);
+  for (int64_t k = 0; k < nbr; ++k) {
+    int f = brf[k] - base, t = brt[k] - base;
+    if (f < 0 || f >= n || t < 0 || t >= n || f == t) throw std::invalid_argument("sblx_create: branch endpoint out of range");
+    rows[f].push_back(t);
+    rows[t].push_back(f);
+  }
+  H.y_rowptr.assign(n + 1, 0);
+  H.y_col.clear();
+  for (int64_t i = 0; i < n; ++i) {
+    auto& r = rows[i];
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+    for (int c : r) H.y_col.push_back(c);
+    H.y_rowptr[i + 1] = (int)H.y_col.size();
+  }
+  H.y_val.assign(H.y_col.size(), make_double2(0.0, 0.0));
+  if (nzval) {
+    for (int64_t j = 0; j < n; ++j)
+      for (int64_t p = colptr[j] - base; p < colptr[j + 1] - base; ++p) {
+        int i = (int)(rowval[p] - base);
+        auto b = H.y_col.begin() + H.y_rowptr[i], e = H.y_col.begin() + H.y_rowptr[i + 1];
+        auto it = std::lower_bound(b, e, (int)j);
+        size_t pos = it - H.y_col.begin();
+        H.y_val[pos].x += nzval[2 * p];
+        H.y_val[pos].y += nzval[2 * p + 1];
+      }
+  }
+}
+
+static void build_nodes_and_symbolic(HostModel& H, const sblx_options& o) {
+  const int n = H.n;
+  H.node_of_bus.assign(n, -1);
+  H.bus_of_node.clear();
+  for (int i = 0; i < n; ++i)
+    if (i != H.slack) {
+      H.node_of_bus[i] = (int)H.bus_of_node.size();
+      H.bus_of_node.push_back(i);
+    }
+  H.m = n - 1;
+  H.jb_rowptr.assign(H.m + 1, 0);
+  H.jb_row.clear();
+  H.jb_col.clear();
+  H.jb_ypos.clear();
+  for (int a = 0; a < H.m; ++a) {
+    int i = H.bus_of_node[a];
+    for (int p = H.y_rowptr[i]; p < H.y_rowptr[i + 1]; ++p) {
+      int j = H.y_col[p];
+      if (j == H.slack) continue;
+      H.jb_row.push_back(a);
+      H.jb_col.push_back(H.node_of_bus[j]);
+      H.jb_ypos.push_back(p);
+    }
+    H.jb_rowptr[a + 1] = (int64_t)H.jb_col.size();
+  }
+  SymbolicOptions so;
+  so.ordering = o.ordering;
+  so.relax_zero_frac = o.relax_zero_frac;
+  analyze(H.m, H.jb_rowptr, H.jb_col, so, H.sym);
+}
+
+// Plain C++ walk over the same panels / index maps as k_front + k_backsolve (symbolic self-test).
+static double host_selftest(const HostModel& H, uint64_t seed) {
+  const Symbolic& S = H.sym;
+  const int m = H.m;
+  const int64_t nnzB = (int64_t)H.jb_col.size();
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> ud(-1.0, 1.0);
+  std::vector<double> Jv(nnzB * 4);
+  std::vector<double> b(2 * m), x(2 * m, 0.0);
+  for (int a = 0; a < m; ++a) {
+    int cnt = (int)(H.jb_rowptr[a + 1] - H.jb_rowptr[a]);
+    for (int64_t k = H.jb_rowptr[a]; k < H.jb_rowptr[a + 1]; ++k) {
+      for (int q = 0; q < 4; ++q) Jv[4 * k + q] = ud(rng);
+      if (H.jb_col[k] == a) {  // off-diagonal-dominant 2x2 pivot like the real Jacobian
+        Jv[4 * k + 0] = 0.1 * ud(rng);
+        Jv[4 * k + 3] = 0.1 * ud(rng);
+        Jv[4 * k + 1] = 4.0 * cnt + ud(rng);
+        Jv[4 * k + 2] = 4.0 * cnt + ud(rng);
+      }
+    }
+  }
+  for (auto& v : b) v = ud(rng);
+  // rhs in elimination order
+  std::vector<double> rhs(2 * m), yv(2 * m), xv(2 * m);
+  for (int a = 0; a < m; ++a) {
+    rhs[2 * S.iperm[a]] = b[2 * a];
+    rhs[2 * S.iperm[a] + 1] = b[2 * a + 1];
+  }
+  std::vector<double> U((size_t)S.u_blocks * 4, 0.0), C((size_t)S.c_blocks * 4 + 8, 0.0);
+  auto mm_sub = [](double* t, const double* a, const double* u) {
+    t[0] -= a[0] * u[0] + a[1] * u[2];
+    t[1] -= a[0] * u[1] + a[1] * u[3];
+    t[2] -= a[2] * u[0] + a[3] * u[2];
+    t[3] -= a[2] * u[1] + a[3] * u[3];
+  };
+  const int np = (int)S.panels.size();
+  for (int l = 0; l < S.nlevels; ++l)
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      const int pi = S.level_panels[q];
+      const Panel& P = S.panels[pi];
+      const int w = P.w, h = P.h, nf = w + h;
+      std::vector<double> T((size_t)w * nf * 4, 0.0), Lp((size_t)h * w * 4, 0.0), b1(2 * w, 0.0);
+      for (int64_t k = 0; k < P.asm_cnt; ++k) {
+        int src = S.asm_src[P.asm_ptr + k], dst = S.asm_dst[P.asm_ptr + k];
+        double* d = dst < w * nf ? &T[(size_t)dst * 4] : &Lp[(size_t)(dst - w * nf) * 4];
+        for (int z = 0; z < 4; ++z) d[z] = Jv[4 * (size_t)src + z];
+      }
+      for (int p = 0; p < w; ++p) { b1[2 * p] = rhs[2 * (P.first + p)]; b1[2 * p + 1] = rhs[2 * (P.first + p) + 1]; }
+      for (int ci = 0; ci < P.nchild; ++ci) {
+        int c = S.child_list[P.child_ptr + ci];
+        const Panel& Cp = S.panels[c];
+        const int hc = Cp.h, kc = S.kpiv[c];
+        const int* rel = &S.rel[S.rel_ptr[c]];
+        const double* Cm = &C[(size_t)Cp.c_off * 4];
+        const double* cv = Cm + (size_t)hc * hc * 4;
+        for (int a = 0; a < hc; ++a)
+          for (int bb = 0; bb < hc; ++bb) {
+            if (a >= kc && bb >= kc) continue;
+            int la = rel[a], lb = rel[bb];
+            double* d = la < w ? &T[((size_t)la * nf + lb) * 4] : &Lp[((size_t)(la - w) * w + lb) * 4];
+            for (int z = 0; z < 4; ++z) d[z] += Cm[((size_t)a * hc + bb) * 4 + z];
+          }
+        for (int a = 0; a < kc; ++a) { b1[2 * rel[a]] += cv[2 * a]; b1[2 * rel[a] + 1] += cv[2 * a + 1]; }
+      }
+      for (int p = 0; p < w; ++p) {
+        double* d = &T[((size_t)p * nf + p) * 4];
+        double det = d[0] * d[3] - d[1] * d[2];
+        double D[4] = {d[3] / det, -d[1] / det, -d[2] / det, d[0] / det};
+        for (int c = p + 1; c < nf; ++c) {
+          double* u = &T[((size_t)p * nf + c) * 4];
+          double t[4] = {D[0] * u[0] + D[1] * u[2], D[0] * u[1] + D[1] * u[3], D[2] * u[0] + D[3] * u[2], D[2] * u[1] + D[3] * u[3]};
+          for (int z = 0; z < 4; ++z) u[z] = t[z];
+        }
+        double y0 = D[0] * b1[2 * p] + D[1] * b1[2 * p + 1], y1 = D[2] * b1[2 * p] + D[3] * b1[2 * p + 1];
+        b1[2 * p] = y0; b1[2 * p + 1] = y1;
+        for (int i = p + 1; i < w; ++i) {
+          const double* a = &T[((size_t)i * nf + p) * 4];
+          for (int c = p + 1; c < nf; ++c) mm_sub(&T[((size_t)i * nf + c) * 4], a, &T[((size_t)p * nf + c) * 4]);
+          b1[2 * i] -= a[0] * y0 + a[1] * y1;
+          b1[2 * i + 1] -= a[2] * y0 + a[3] * y1;
+        }
+        for (int a = 0; a < h; ++a) {
+          const double* lv = &Lp[((size_t)a * w + p) * 4];
+          for (int c = p + 1; c < w; ++c) mm_sub(&Lp[((size_t)a * w + c) * 4], lv, &T[((size_t)p * nf + c) * 4]);
+        }
+      }
+      std::copy(T.begin(), T.end(), U.begin() + (size_t)P.u_off * 4);
+      for (int p = 0; p < w; ++p) { yv[2 * (P.first + p)] = b1[2 * p]; yv[2 * (P.first + p) + 1] = b1[2 * p + 1]; }
+      double* Co = &C[(size_t)P.c_off * 4];
+      double* cvo = Co + (size_t)h * h * 4;
+      for (int a = 0; a < h; ++a) {
+        for (int bb = 0; bb < h; ++bb) {
+          double acc[4] = {0, 0, 0, 0};
+          for (int p = 0; p < w; ++p) mm_sub(acc, &Lp[((size_t)a * w + p) * 4], &T[((size_t)p * nf + w + bb) * 4]);
+          for (int ci = 0; ci < P.nchild; ++ci) {
+            int c = S.child_list[P.child_ptr + ci];
+            const Panel& Cp = S.panels[c];
+            const int* inv = &S.inv[S.inv_ptr[P.child_ptr + ci]];
+            if (inv[a] >= 0 && inv[bb] >= 0)
+              for (int z = 0; z < 4; ++z) acc[z] += C[(size_t)Cp.c_off * 4 + ((size_t)inv[a] * Cp.h + inv[bb]) * 4 + z];
+          }
+          for (int z = 0; z < 4; ++z) Co[((size_t)a * h + bb) * 4 + z] = acc[z];
+        }
+        double v0 = 0, v1 = 0;
+        for (int p = 0; p < w; ++p) {
+          const double* lv = &Lp[((size_t)a * w + p) * 4];
+          v0 -= lv[0] * b1[2 * p] + lv[1] * b1[2 * p + 1];
+          v1 -= lv[2] * b1[2 * p] + lv[3] * b1[2 * p + 1];
+        }
+        for (int ci = 0; ci < P.nchild; ++ci) {
+          int c = S.child_list[P.child_ptr + ci];
+          const Panel& Cp = S.panels[c];
+          int ia = S.inv[S.inv_ptr[P.child_ptr + ci] + a];
+          if (ia >= 0) {
+            const double* cvc = &C[(size_t)Cp.c_off * 4 + (size_t)Cp.h * Cp.h * 4];
+            v0 += cvc[2 * ia];
+            v1 += cvc[2 * ia + 1];
+          }
+        }
+        cvo[2 * a] = v0;
+        cvo[2 * a + 1] = v1;
+      }
+    }
+  (void)np;
+  for (int l = S.nlevels - 1; l >= 0; --l)
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      const Panel& P = S.panels[S.level_panels[q]];
+      const int w = P.w, h = P.h, nf = w + h;
+      const double* Up = &U[(size_t)P.u_off * 4];
+      for (int p = w - 1; p >= 0; --p) {
+        double a0 = yv[2 * (P.first + p)], a1 = yv[2 * (P.first + p) + 1];
+        for (int c = p + 1; c < nf; ++c) {
+          int g = c < w ? P.first + c : S.struct_nodes[P.struct_ptr + (c - w)];
+          const double* u = &Up[((size_t)p * nf + c) * 4];
+          a0 -= u[0] * xv[2 * g] + u[1] * xv[2 * g + 1];
+          a1 -= u[2] * xv[2 * g] + u[3] * xv[2 * g + 1];
+        }
+        xv[2 * (P.first + p)] = a0;
+        xv[2 * (P.first + p) + 1] = a1;
+      }
+    }
+  for (int a = 0; a < m; ++a) { x[2 * a] = xv[2 * S.iperm[a]]; x[2 * a + 1] = xv[2 * S.iperm[a] + 1]; }
+  // residual
+  double rn = 0, bn = 0;
+  for (int a = 0; a < m; ++a) {
+    double r0 = -b[2 * a], r1 = -b[2 * a + 1];
+    for (int64_t k = H.jb_rowptr[a]; k < H.jb_rowptr[a + 1]; ++k) {
+      int c = H.jb_col[k];
+      r0 += Jv[4 * k] * x[2 * c] + Jv[4 * k + 1] * x[2 * c + 1];
+      r1 += Jv[4 * k + 2] * x[2 * c] + Jv[4 * k + 3] * x[2 * c + 1];
+    }
+    rn = std::max(rn, std::max(std::fabs(r0), std::fabs(r1)));
+    bn = std::max(bn, std::max(std::fabs(b[2 * a]), std::fabs(b[2 * a + 1])));
+  }
+  return rn / std::max(bn, 1e-300);
+}
+
+// ------------------------------------------------------------------------------------------
+struct LaunchGroup {
+  int off, cnt, nt, smem;     // range in d_level_panels, threads, dynamic smem bytes
+};
+
+struct HostResults {
+  std::vector<int> conv, status, iter, nsw, islands;
+  std::vector<double> fm, vmin, vmax, load;
+};
+
+}  // namespace sblx
+
+using namespace sblx;
+
+struct sblx_handle {
+  sblx_options opt{};
+  HostModel H;
+  std::string err;
+  std::mutex mu;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool cuda_ready = false;
+  // device model
+  DevBuf<int> d_y_rowptr, d_y_col, d_node_of_bus, d_bus_of_node, d_elim_of_node, d_node_of_elim, d_jb_row, d_jb_col, d_jb_ypos;
+  DevBuf<double2> d_y_val, d_S0, d_V0, d_y11, d_y12, d_y21, d_y22;
+  DevBuf<double> d_vset, d_qmin, d_qmax, d_qload, d_rating;
+  DevBuf<unsigned char> d_type0, d_lock, d_br_status;
+  DevBuf<int> d_br_from, d_br_to;
+  DevBuf<PanelDev> d_panels;
+  DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels;
+  DevBuf<long long> d_rel_ptr, d_inv_ptr;
+  std::vector<std::vector<LaunchGroup>> front_groups;   // per level
+  std::vector<std::vector<LaunchGroup>> solve_groups;
+  DevModel M{};
+  // slots
+  int W = 0;
+  size_t bytes_per_slot = 0;
+  DevBuf<double2> s_V, s_I, s_S, s_rhs, s_yv, s_xv;
+  DevBuf<double> s_qload, s_Jv, s_U, s_C, s_fm;
+  DevBuf<unsigned char> s_type, s_iso, s_evcnt, s_evact;
+  DevBuf<short> s_evlast;
+  DevBuf<int> s_scen, s_iter, s_state, s_changed, s_nev, s_singular, s_numerical, s_reason, s_viol, s_maxsw, s_rated, s_out_cnt, s_out_br;
+  DevBuf<unsigned long long> s_mis, s_mis2, s_pvres, s_vminb, s_vmaxb, s_loadb;
+  DevBuf<int> l_active, l_fresh, l_step, l_fin, l_counts;
+  Slots A{};
+  Lists L{};
+  // staged batch
+  int64_t B = 0;
+  bool staged = false, ran = false, sweep_q = false;
+  DevBuf<int> b_queue, b_out_ptr, b_out_br, b_iso_ptr, b_iso_bus;
+  DevBuf<double2> b_S, b_Vstart;
+  DevBuf<double> b_ql;
+  DevBuf<int> r_conv, r_status, r_iter, r_nsw;
+  DevBuf<double> r_fm, r_vmin, r_vmax, r_load;
+  DevBuf<double2> r_V;
+  DevBuf<unsigned char> r_types, r_summary;
+  Batch Bt{};
+  HostResults hostres;       // host-decided scenarios (islanded / bad branch), status < 0 = solved on device
+  int64_t nq = 0;
+  int* pinned_counts = nullptr;
+  sblx_stats stats{};
+  cudaEvent_t ev[8] = {};
+
+  ~sblx_handle() {
+    if (cuda_ready) {
+      cudaSetDevice(device);
+      for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+      if (pinned_counts) cudaFreeHost(pinned_counts);
+      if (stream) cudaStreamDestroy(stream);
+    }
+  }
+};
+
+namespace sblx {
+
+static void upload_model(sblx_handle* h) {
+  HostModel& H = h->H;
+  cudaStream_t s = h->stream;
+  const Symbolic& S = H.sym;
+  h->d_y_rowptr.upload(H.y_rowptr, s);
+  h->d_y_col.upload(H.y_col, s);
+  h->d_y_val.upload(H.y_val, s);
+  h->d_node_of_bus.upload(H.node_of_bus, s);
+  h->d_bus_of_node.upload(H.bus_of_node, s);
+  h->d_elim_of_node.upload(S.iperm, s);
+  h->d_node_of_elim.upload(S.perm, s);
+  h->d_jb_row.upload(H.jb_row, s);
+  h->d_jb_col.upload(H.jb_col, s);
+  h->d_jb_ypos.upload(H.jb_ypos, s);
+  h->d_S0.upload(H.S0, s);
+  h->d_V0.upload(H.V0, s);
+  h->d_vset.upload(H.vset, s);
+  h->d_qmin.upload(H.qmin, s);
+  h->d_qmax.upload(H.qmax, s);
+  h->d_qload.upload(H.qload, s);
+  h->d_type0.upload(H.type0, s);
+  h->d_lock.upload(H.lockmask, s);
+  h->d_br_from.upload(H.br_from, s);
+  h->d_br_to.upload(H.br_to, s);
+  h->d_y11.upload(H.y11, s);
+  h->d_y12.upload(H.y12, s);
+  h->d_y21.upload(H.y21, s);
+  h->d_y22.upload(H.y22, s);
+  h->d_rating.upload(H.rating, s);
+  h->d_br_status.upload(H.br_status, s);
+  std::vector<PanelDev> pd(S.panels.size());
+  for (size_t i = 0; i < pd.size(); ++i) {
+    const Panel& P = S.panels[i];
+    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.asm_ptr, (int)P.asm_cnt, (long long)P.u_off, (long long)P.c_off};
+  }
+  h->d_panels.upload(pd, s);
+  h->d_struct.upload(S.struct_nodes, s);
+  h->d_child.upload(S.child_list, s);
+  h->d_rel.upload(S.rel, s);
+  h->d_kpiv.upload(S.kpiv, s);
+  h->d_inv.upload(S.inv, s);
+  h->d_asm_src.upload(S.asm_src, s);
+  h->d_asm_dst.upload(S.asm_dst, s);
+  std::vector<long long> rp(S.rel_ptr.begin(), S.rel_ptr.end()), ip(S.inv_ptr.begin(), S.inv_ptr.end());
+  h->d_rel_ptr.upload(rp, s);
+  h->d_inv_ptr.upload(ip, s);
+  // launch groups: per level, panels sorted by size class
+  auto front_class = [](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 72 * 1024 ? 2 : 3; };
+  static const int front_nt[4] = {32, 64, 128, 256};
+  std::vector<int> lp;
+  h->front_groups.assign(S.nlevels, {});
+  h->solve_groups.assign(S.nlevels, {});
+  for (int l = 0; l < S.nlevels; ++l) {
+    std::vector<int> ids(S.level_panels.begin() + S.level_ptr[l], S.level_panels.begin() + S.level_ptr[l + 1]);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
+      return front_class(panel_smem_bytes(S.panels[a].w, S.panels[a].h)) < front_class(panel_smem_bytes(S.panels[b].w, S.panels[b].h));
+    });
+    size_t i = 0;
+    while (i < ids.size()) {
+      int c = front_class(panel_smem_bytes(S.panels[ids[i]].w, S.panels[ids[i]].h));
+      size_t j = i;
+      int smem = 0, hs = 0;
+      while (j < ids.size() && front_class(panel_smem_bytes(S.panels[ids[j]].w, S.panels[ids[j]].h)) == c) {
+        smem = std::max(smem, panel_smem_bytes(S.panels[ids[j]].w, S.panels[ids[j]].h));
+        hs = std::max(hs, S.panels[ids[j]].h + S.panels[ids[j]].w);
+        ++j;
+      }
+      LaunchGroup g{(int)lp.size() + (int)i, (int)(j - i), front_nt[c], smem};
+      h->front_groups[l].push_back(g);
+      LaunchGroup gs{g.off, g.cnt, hs <= 32 ? 32 : hs <= 96 ? 64 : 128, hs * 16 + 64};
+      h->solve_groups[l].push_back(gs);
+      i = j;
+    }
+    lp.insert(lp.end(), ids.begin(), ids.end());
+  }
+  h->d_level_panels.upload(lp, s);
+  CK(cudaStreamSynchronize(s));
+  // opt-in shared memory
+  CK(cudaFuncSetAttribute(k_front<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024));
+  CK(cudaFuncSetAttribute(k_front<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+  CK(cudaFuncSetAttribute(k_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  CK(cudaFuncSetAttribute(k_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CK(cudaFuncSetAttribute(k_backsolve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(k_backsolve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(k_backsolve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+
+  DevModel& M = h->M;
+  M.n = H.n; M.m = H.m; M.slack = H.slack; M.nbr = H.nbr; M.nnzB = (int)H.jb_col.size(); M.W = 0;
+  M.y_rowptr = h->d_y_rowptr.p; M.y_col = h->d_y_col.p; M.y_val = h->d_y_val.p;
+  M.node_of_bus = h->d_node_of_bus.p; M.bus_of_node = h->d_bus_of_node.p;
+  M.elim_of_node = h->d_elim_of_node.p; M.node_of_elim = h->d_node_of_elim.p;
+  M.jb_row = h->d_jb_row.p; M.jb_col = h->d_jb_col.p; M.jb_ypos = h->d_jb_ypos.p;
+  M.S0 = h->d_S0.p; M.V0 = h->d_V0.p; M.vset = h->d_vset.p; M.qmin = h->d_qmin.p; M.qmax = h->d_qmax.p;
+  M.qload = h->d_qload.p; M.type0 = h->d_type0.p; M.lockmask = h->d_lock.p;
+  M.br_from = h->d_br_from.p; M.br_to = h->d_br_to.p; M.y11 = h->d_y11.p; M.y12 = h->d_y12.p; M.y21 = h->d_y21.p; M.y22 = h->d_y22.p;
+  M.rating = h->d_rating.p; M.br_status = h->d_br_status.p;
+  M.panels = h->d_panels.p; M.struct_nodes = h->d_struct.p; M.child_list = h->d_child.p; M.rel = h->d_rel.p;
+  M.rel_ptr = h->d_rel_ptr.p; M.kpiv = h->d_kpiv.p; M.inv = h->d_inv.p; M.inv_ptr = h->d_inv_ptr.p;
+  M.asm_src = h->d_asm_src.p; M.asm_dst = h->d_asm_dst.p;
+  M.u_blocks = S.u_blocks; M.c_blocks = S.c_blocks + 2;
+  const sblx_options& o = h->opt;
+  M.tol = o.tol; M.damp = o.damp; M.hyst = o.q_hyst_pu; M.vm_min = o.vm_min_pu; M.vm_max = o.vm_max_pu; M.base_mva = o.base_mva;
+  M.max_iter = o.max_iter; M.qlim_enabled = o.qlimits_enabled; M.qlim_start = o.qlimit_start_iter; M.cooldown = o.cooldown_iters;
+  M.guard = o.guard_max_switches; M.freeze = o.freeze_after_repeated_switching;
+  M.allow_reenable = (o.cooldown_iters > 0) || (o.q_hyst_pu > 0.0);   // rectangular_network_solver.jl:663-665
+}
+
+static size_t slot_bytes(const HostModel& H) {
+  const Symbolic& S = H.sym;
+  size_t n = H.n, m = H.m;
+  return n * (16 * 3 + 8 + 4 + 2) + m * 16 * 3 + (size_t)H.jb_col.size() * 32 + (size_t)(S.u_blocks + S.c_blocks + 2) * 32 +
+         (size_t)MAXOUT * 4 + 200;
+}
+
+static void ensure_cuda(sblx_handle* h) {
+  if (h->cuda_ready) {
+    CK(cudaSetDevice(h->device));
+    return;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) throw CudaError("no CUDA device available (libsblx has no CPU fallback)");
+  int dev = h->opt.device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  if (dev >= ndev) throw std::invalid_argument("sblx: device ordinal out of range");
+  CK(cudaSetDevice(dev));
+  h->device = dev;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+  CK(cudaMallocHost(&h->pinned_counts, 8 * sizeof(int)));
+  h->cuda_ready = true;
+  upload_model(h);
+}
+
+static void ensure_slots(sblx_handle* h, int64_t want) {
+  HostModel& H = h->H;
+  size_t freeb = 0, totalb = 0;
+  CK(cudaMemGetInfo(&freeb, &totalb));
+  h->bytes_per_slot = slot_bytes(H);
+  // memory already held by the current slot set counts as available
+  size_t avail = freeb + (size_t)h->W * h->bytes_per_slot;
+  int64_t cap = (int64_t)((double)avail * h->opt.mem_fraction / (double)h->bytes_per_slot);
+  cap = std::min<int64_t>(cap, 32768);
+  if (h->opt.max_slots > 0) cap = std::min<int64_t>(cap, h->opt.max_slots);
+  cap = std::max<int64_t>(cap, 1);
+  int64_t W = std::min<int64_t>(cap, std::max<int64_t>(want, 1));
+  W = std::min<int64_t>(cap, (W + 31) / 32 * 32);
+  if (W <= h->W) return;
+  const size_t n = H.n, m = H.m, nw = n * (size_t)W;
+  h->s_V.alloc(nw); h->s_I.alloc(nw); h->s_S.alloc(nw); h->s_qload.alloc(nw);
+  h->s_type.alloc(nw); h->s_iso.alloc(nw); h->s_evcnt.alloc(nw); h->s_evact.alloc(nw); h->s_evlast.alloc(nw);
+  h->s_rhs.alloc(m * W); h->s_yv.alloc(m * W); h->s_xv.alloc(m * W);
+  h->s_Jv.alloc((size_t)H.jb_col.size() * 4 * W);
+  h->s_U.alloc((size_t)h->M.u_blocks * 4 * W);
+  h->s_C.alloc((size_t)h->M.c_blocks * 4 * W);
+  h->s_scen.alloc(W); h->s_iter.alloc(W); h->s_state.alloc(W); h->s_changed.alloc(W); h->s_nev.alloc(W);
+  h->s_singular.alloc(W); h->s_numerical.alloc(W); h->s_reason.alloc(W); h->s_viol.alloc(W); h->s_maxsw.alloc(W);
+  h->s_rated.alloc(W); h->s_out_cnt.alloc(W); h->s_out_br.alloc((size_t)W * MAXOUT); h->s_fm.alloc(W);
+  h->s_mis.alloc(W); h->s_mis2.alloc(W); h->s_pvres.alloc(W); h->s_vminb.alloc(W); h->s_vmaxb.alloc(W); h->s_loadb.alloc(W);
+  h->l_active.alloc(W); h->l_fresh.alloc(W); h->l_step.alloc(W); h->l_fin.alloc(W); h->l_counts.alloc(8);
+  h->W = (int)W;
+  h->M.W = (int)W;
+  Slots& A = h->A;
+  A.V = h->s_V.p; A.I = h->s_I.p; A.S = h->s_S.p; A.qload_s = nullptr;
+  A.type = h->s_type.p; A.iso = h->s_iso.p; A.evcnt = h->s_evcnt.p; A.evact = h->s_evact.p; A.evlast = h->s_evlast.p;
+  A.rhs = h->s_rhs.p; A.Jv = h->s_Jv.p; A.U = h->s_U.p; A.C = h->s_C.p; A.yv = h->s_yv.p; A.xv = h->s_xv.p;
+  A.scen = h->s_scen.p; A.iter = h->s_iter.p; A.state = h->s_state.p; A.changed = h->s_changed.p; A.nev = h->s_nev.p;
+  A.singular = h->s_singular.p; A.numerical = h->s_numerical.p; A.reason = h->s_reason.p;
+  A.mis_bits = h->s_mis.p; A.mis2_bits = h->s_mis2.p; A.fm = h->s_fm.p;
+  A.pvres_bits = h->s_pvres.p; A.vmin_bits = h->s_vminb.p; A.vmax_bits = h->s_vmaxb.p; A.load_bits = h->s_loadb.p;
+  A.viol = h->s_viol.p; A.maxsw = h->s_maxsw.p; A.rated = h->s_rated.p; A.out_cnt = h->s_out_cnt.p; A.out_br = h->s_out_br.p;
+  Lists& L = h->L;
+  L.active = h->l_active.p; L.fresh = h->l_fresh.p; L.step = h->l_step.p; L.fin = h->l_fin.p; L.counts = h->l_counts.p;
+}
+
+// ------------------------------------------------------------------------------------------
+// host topology analysis per scenario: isolated buses (network.jl:1881-1930) and islands
+// (ac_islands.jl:50-93, rectangular_network_solver.jl:1914-1935)
+// ------------------------------------------------------------------------------------------
+static void build_topology(HostModel& H) {
+  const int n = H.n;
+  H.deg.assign(n, 0);
+  for (int k = 0; k < H.nbr; ++k)
+    if (H.br_status[k]) { H.deg[H.br_from[k]]++; H.deg[H.br_to[k]]++; }
+  H.adj_ptr.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) H.adj_ptr[i + 1] = H.adj_ptr[i] + H.deg[i];
+  H.adj_nb.assign(H.adj_ptr[n], 0);
+  H.adj_br.assign(H.adj_ptr[n], 0);
+  std::vector<int> fill(H.adj_ptr.begin(), H.adj_ptr.end() - 1);
+  for (int k = 0; k < H.nbr; ++k)
+    if (H.br_status[k]) {
+      int f = H.br_from[k], t = H.br_to[k];
+      H.adj_nb[fill[f]] = t; H.adj_br[fill[f]++] = k;
+      H.adj_nb[fill[t]] = f; H.adj_br[fill[t]++] = k;
+    }
+  H.base_iso.clear();
+  for (int i = 0; i < n; ++i)
+    if (H.deg[i] == 0) H.base_iso.push_back(i);
+}
+
+struct TopoScratch {
+  std::vector<int> markA, markB, parent;
+  int stamp = 0;
+  std::vector<int> qa, qb;
+};
+
+// returns island count; fills iso (sorted). status_out: -1 = solve on device, else SBLX_ST_*
+static int analyze_scenario(const HostModel& H, const int* out, int nout, TopoScratch& ts, std::vector<int>& iso, int& status_out) {
+  const int n = H.n;
+  iso = H.base_iso;
+  status_out = -1;
+  auto removed = [&](int br) {
+    for (int q = 0; q < nout; ++q)
+      if (out[q] == br) return true;
+    return false;
+  };
+  // isolated endpoints
+  for (int q = 0; q < nout; ++q) {
+    const int br = out[q];
+    if (!H.br_status[br]) continue;
+    for (int u : {H.br_from[br], H.br_to[br]}) {
+      int rem = 0;
+      for (int p = H.adj_ptr[u]; p < H.adj_ptr[u + 1]; ++p)
+        if (!removed(H.adj_br[p])) ++rem;
+      if (rem == 0 && std::find(iso.begin(), iso.end(), u) == iso.end()) iso.push_back(u);
+    }
+  }
+  std::sort(iso.begin(), iso.end());
+  auto is_iso = [&](int u) { return std::binary_search(iso.begin(), iso.end(), u); };
+  bool need_full = H.base_islands != 1;
+  if (!need_full) {
+    if ((int)ts.markA.size() != n) { ts.markA.assign(n, 0); ts.markB.assign(n, 0); }
+    for (int q = 0; q < nout && !need_full; ++q) {
+      const int br = out[q];
+      if (!H.br_status[br]) continue;
+      const int u = H.br_from[br], v = H.br_to[br];
+      if (is_iso(u) || is_iso(v)) continue;
+      // bidirectional BFS u <-> v in the graph minus the outage set
+      const int sa = ++ts.stamp, sb = ++ts.stamp;
+      ts.qa.assign(1, u); ts.qb.assign(1, v);
+      ts.markA[u] = sa; ts.markB[v] = sb;
+      size_t ia = 0, ib = 0;
+      bool met = false;
+      while (!met) {
+        const bool canA = ia < ts.qa.size(), canB = ib < ts.qb.size();
+        if (!canA || !canB) break;   // one side exhausted its component without meeting the other
+        const bool expandA = (ts.qa.size() - ia) <= (ts.qb.size() - ib);
+        std::vector<int>& qx = expandA ? ts.qa : ts.qb;
+        size_t& ix = expandA ? ia : ib;
+        std::vector<int>& mine = expandA ? ts.markA : ts.markB;
+        std::vector<int>& other = expandA ? ts.markB : ts.markA;
+        const int sm = expandA ? sa : sb, so = expandA ? sb : sa;
+        const int x = qx[ix++];
+        for (int p = H.adj_ptr[x]; p < H.adj_ptr[x + 1]; ++p) {
+          if (removed(H.adj_br[p])) continue;
+          const int y = H.adj_nb[p];
+          if (other[y] == so) { met = true; break; }
+          if (mine[y] != sm) { mine[y] = sm; qx.push_back(y); }
+        }
+      }
+      if (!met) need_full = true;
+    }
+    if (!need_full) {
+      // the slack must not be isolated
+      if (is_iso(H.slack)) { status_out = SBLX_ST_ISLANDED_NO_REF; }
+      return 1;
+    }
+  }
+  // full component analysis
+  ts.parent.resize(n);
+  for (int i = 0; i < n; ++i) ts.parent[i] = i;
+  auto find = [&](int i) {
+    while (ts.parent[i] != i) { ts.parent[i] = ts.parent[ts.parent[i]]; i = ts.parent[i]; }
+    return i;
+  };
+  // buses without any in-service branch in the base grid are isolated too
+  std::vector<char> isov(n, 0);
+  for (int u : iso) isov[u] = 1;
+  for (int i = 0; i < n; ++i)
+    if (H.deg[i] == 0) { isov[i] = 1; }
+  for (int k = 0; k < H.nbr; ++k) {
+    if (!H.br_status[k] || removed(k)) continue;
+    int a = find(H.br_from[k]), b = find(H.br_to[k]);
+    if (a != b) { if (a < b) ts.parent[b] = a; else ts.parent[a] = b; }
+  }
+  std::vector<char> has_ref(n, 0);
+  int comps = 0;
+  for (int i = 0; i < n; ++i) {
+    if (isov[i]) continue;
+    int r = find(i);
+    if (r == i) ++comps;
+    if (H.type0[i] == T_SLACK || H.type0[i] == T_PV) has_ref[r] = 1;
+  }
+  if (comps > 1) {
+    bool all_ref = true;
+    for (int i = 0; i < n; ++i)
+      if (!isov[i] && find(i) == i && !has_ref[i]) all_ref = false;
+    status_out = all_ref ? SBLX_ST_ISLANDED_UNSUPPORTED : SBLX_ST_ISLANDED_NO_REF;
+  } else if (isov[H.slack]) {
+    status_out = SBLX_ST_ISLANDED_NO_REF;
+  }
+  return comps;
+}
+
+// ------------------------------------------------------------------------------------------
+static void alloc_results(sblx_handle* h, int64_t B, bool want_v, bool want_types) {
+  h->r_conv.alloc(B); h->r_status.alloc(B); h->r_iter.alloc(B); h->r_nsw.alloc(B);
+  h->r_fm.alloc(B); h->r_vmin.alloc(B); h->r_vmax.alloc(B); h->r_load.alloc(B);
+  if (want_v) h->r_V.alloc((size_t)B * h->H.n); else h->r_V.release();
+  if (want_types) h->r_types.alloc((size_t)B * h->H.n); else h->r_types.release();
+  CK(cudaMemsetAsync(h->r_conv.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->r_status.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->r_iter.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->r_nsw.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->r_fm.p, 0xff, B * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->r_vmin.p, 0xff, B * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->r_vmax.p, 0xff, B * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->r_load.p, 0xff, B * sizeof(double), h->stream));
+  if (want_v) CK(cudaMemsetAsync(h->r_V.p, 0, (size_t)B * h->H.n * sizeof(double2), h->stream));
+  if (want_types) CK(cudaMemsetAsync(h->r_types.p, 0, (size_t)B * h->H.n, h->stream));
+}
+
+static void set_batch(sblx_handle* h) {
+  Batch& Bt = h->Bt;
+  Bt.B = (int)h->B; Bt.nq = (int)h->nq; Bt.use_sweep_q = h->sweep_q;
+  Bt.queue = h->b_queue.p; Bt.out_ptr = h->b_out_ptr.p; Bt.out_br = h->b_out_br.p;
+  Bt.iso_ptr = h->b_iso_ptr.p; Bt.iso_bus = h->b_iso_bus.p;
+  Bt.Ssweep = h->b_S.p; Bt.qlsweep = h->b_ql.p; Bt.Vstart = h->b_Vstart.p;
+  Bt.r_conv = h->r_conv.p; Bt.r_status = h->r_status.p; Bt.r_iter = h->r_iter.p; Bt.r_nsw = h->r_nsw.p;
+  Bt.r_fm = h->r_fm.p; Bt.r_vmin = h->r_vmin.p; Bt.r_vmax = h->r_vmax.p; Bt.r_load = h->r_load.p;
+  Bt.r_V = h->r_V.p; Bt.r_types = h->r_types.p;
+  h->A.qload_s = h->sweep_q ? h->s_qload.p : nullptr;
+}
+
+static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const int32_t* obr, bool want_v, bool want_types) {
+  ensure_cuda(h);
+  const double t0 = now_ms();
+  HostModel& H = h->H;
+  const int base = h->opt.index_base;
+  h->B = B;
+  h->sweep_q = false;
+  HostResults& R = h->hostres;
+  R.status.assign(B, -1);
+  R.islands.assign(B, 1);
+  std::vector<int> out_ptr(B + 1, 0), out_br;
+  std::vector<int> iso_ptr(B + 1, 0), iso_bus;
+  std::vector<std::vector<int>> iso_per(B);
+  if (optr) {
+    out_br.reserve(optr[B]);
+    for (int64_t s = 0; s < B; ++s) {
+      for (int q = optr[s]; q < optr[s + 1]; ++q) {
+        int br = obr[q] - base;
+        if (br < 0 || br >= H.nbr) { R.status[s] = SBLX_ST_BAD_BRANCH; continue; }
+        out_br.push_back(br);
+      }
+      out_ptr[s + 1] = (int)out_br.size();
+      if (out_ptr[s + 1] - out_ptr[s] > MAXOUT) R.status[s] = SBLX_ST_BAD_BRANCH;
+    }
+  }
+  // topology analysis, threaded over scenarios
+  {
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (B < 256) nt = 1;
+    std::vector<std::thread> th;
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+      TopoScratch ts;
+      std::vector<int> iso;
+      for (;;) {
+        int64_t s0 = next.fetch_add(64);
+        if (s0 >= B) break;
+        for (int64_t s = s0; s < std::min<int64_t>(B, s0 + 64); ++s) {
+          if (R.status[s] == SBLX_ST_BAD_BRANCH) { R.islands[s] = 0; continue; }
+          int st;
+          R.islands[s] = analyze_scenario(H, out_br.data() + out_ptr[s], out_ptr[s + 1] - out_ptr[s], ts, iso, st);
+          R.status[s] = st;
+          iso_per[s] = iso;
+        }
+      }
+    };
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  std::vector<int> queue;
+  queue.reserve(B);
+  for (int64_t s = 0; s < B; ++s) {
+    for (int b : iso_per[s]) iso_bus.push_back(b);
+    iso_ptr[s + 1] = (int)iso_bus.size();
+    if (R.status[s] < 0) queue.push_back((int)s);
+  }
+  h->nq = (int64_t)queue.size();
+  const double t1 = now_ms();
+  h->stats = sblx_stats{};
+  h->stats.host_prep_ms = t1 - t0;
+  ensure_slots(h, h->nq);
+  h->b_queue.upload(queue, h->stream);
+  h->b_out_ptr.upload(out_ptr, h->stream);
+  h->b_out_br.upload(out_br, h->stream);
+  h->b_iso_ptr.upload(iso_ptr, h->stream);
+  h->b_iso_bus.upload(iso_bus, h->stream);
+  h->b_S.release(); h->b_ql.release(); h->b_Vstart.release();
+  alloc_results(h, B, want_v, want_types);
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.h2d_bytes = (int64_t)((queue.size() + out_ptr.size() + out_br.size() + iso_ptr.size() + iso_bus.size()) * sizeof(int));
+  h->stats.h2d_ms = now_ms() - t1;
+  set_batch(h);
+  h->staged = true;
+  h->ran = false;
+}
+
+template <int NT>
+static void launch_front(sblx_handle* h, const LaunchGroup& g, int nstep) {
+  dim3 grid(g.cnt, nstep);
+  k_front<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+}
+template <int NT>
+static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
+  dim3 grid(g.cnt, nstep);
+  k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+}
+
+static void run_staged(sblx_handle* h) {
+  if (!h->staged) throw std::invalid_argument("sblx_run_staged: nothing staged");
+  ensure_cuda(h);
+  cudaStream_t s = h->stream;
+  const HostModel& H = h->H;
+  const int W = h->W, n = H.n, m = H.m, nnzB = (int)H.jb_col.size();
+  sblx_stats& st = h->stats;
+  // reset slots
+  CK(cudaMemsetAsync(h->s_state.p, 0, W * sizeof(int), s));
+  CK(cudaMemsetAsync(h->s_scen.p, 0xff, W * sizeof(int), s));
+  CK(cudaMemsetAsync(h->l_counts.p, 0, 8 * sizeof(int), s));
+  cudaEvent_t* ev = h->ev;
+  CK(cudaEventRecord(ev[0], s));
+  int64_t running = 0, qhead = 0;
+  const int64_t nq = h->nq;
+  double t_mis = 0, t_jac = 0, t_fac = 0, t_sol = 0, t_oth = 0;
+  bool have_prev = false;
+  while (running > 0 || qhead < nq) {
+    const int64_t assign = std::min<int64_t>(W - running, nq - qhead);
+    const int nactive_ub = (int)(running + assign);   // exact: DRAIN slots are excluded on the device side
+    CK(cudaEventRecord(ev[1], s));
+    k_assign<<<1, 1024, 0, s>>>(h->M, h->A, h->L, h->Bt);
+    st.launches++;
+    if (assign > 0) {
+      dim3 g((n + 7) / 8, (unsigned)((assign + 31) / 32));
+      k_init<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
+      k_init_iso<<<(unsigned)((assign + 127) / 128), 128, 0, s>>>(h->M, h->A, h->L, h->Bt);
+      st.launches += 2;
+    }
+    {
+      dim3 g((n + 7) / 8, (unsigned)((nactive_ub + 31) / 32));
+      k_mismatch<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+      st.launches++;
+      if (h->opt.qlimits_enabled) {
+        k_qlimit<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+        k_norm<<<nactive_ub, 256, 0, s>>>(h->M, h->A, h->L);
+        st.launches += 2;
+      }
+      k_decide<<<1, 1024, 0, s>>>(h->M, h->A, h->L);
+      st.launches++;
+    }
+    CK(cudaEventRecord(ev[2], s));
+    CK(cudaMemcpyAsync(h->pinned_counts, h->l_counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (have_prev) {
+      float a = 0;
+      CK(cudaEventElapsedTime(&a, ev[3], ev[4])); t_jac += a;
+      CK(cudaEventElapsedTime(&a, ev[4], ev[5])); t_fac += a;
+      CK(cudaEventElapsedTime(&a, ev[5], ev[6])); t_sol += a;
+      CK(cudaEventElapsedTime(&a, ev[6], ev[7])); t_oth += a;
+    }
+    {
+      float a = 0;
+      CK(cudaEventElapsedTime(&a, ev[1], ev[2]));
+      t_mis += a;
+    }
+    const int nactive = h->pinned_counts[0], nstep = h->pinned_counts[2], nfin = h->pinned_counts[3];
+    qhead = h->pinned_counts[4];
+    running += assign;
+    st.ticks++;
+    st.mismatch_evaluations += nactive;
+    st.scenario_iterations += nstep;
+    CK(cudaEventRecord(ev[3], s));
+    if (nstep > 0) {
+      dim3 g((nnzB + 7) / 8, (nstep + 31) / 32);
+      k_jacobian<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+      st.launches++;
+    }
+    CK(cudaEventRecord(ev[4], s));
+    if (nstep > 0) {
+      for (size_t l = 0; l < h->front_groups.size(); ++l)
+        for (const LaunchGroup& g : h->front_groups[l]) {
+          switch (g.nt) {
+            case 32: launch_front<32>(h, g, nstep); break;
+            case 64: launch_front<64>(h, g, nstep); break;
+            case 128: launch_front<128>(h, g, nstep); break;
+            default: launch_front<256>(h, g, nstep); break;
+          }
+          st.launches++;
+          st.factor_launches++;
+        }
+    }
+    CK(cudaEventRecord(ev[5], s));
+    if (nstep > 0) {
+      for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
+        for (const LaunchGroup& g : h->solve_groups[l]) {
+          switch (g.nt) {
+            case 32: launch_solve<32>(h, g, nstep); break;
+            case 64: launch_solve<64>(h, g, nstep); break;
+            default: launch_solve<128>(h, g, nstep); break;
+          }
+          st.launches++;
+        }
+    }
+    CK(cudaEventRecord(ev[6], s));
+    if (nstep > 0) {
+      dim3 g((m + 7) / 8, (nstep + 31) / 32);
+      k_update<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+      k_poststep<<<(nstep + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L);
+      st.launches += 2;
+    }
+    if (nfin > 0) {
+      k_fin_init<<<(nfin + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L);
+      dim3 gb((n + 7) / 8, (nfin + 31) / 32);
+      k_fin_bus<<<gb, dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
+      if (H.nbr > 0) {
+        dim3 gr((H.nbr + 7) / 8, (nfin + 31) / 32);
+        k_fin_branch<<<gr, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+        st.launches++;
+      }
+      k_fin_write<<<(nfin + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L, h->Bt);
+      st.launches += 3;
+      running -= nfin;
+    }
+    CK(cudaEventRecord(ev[7], s));
+    have_prev = true;
+    CK(cudaGetLastError());
+    if (st.ticks > (int64_t)(nq + 8) * (h->opt.max_iter + 2)) throw std::runtime_error("sblx: tick loop did not terminate");
+  }
+  if (h->B > 0) {
+    h->r_summary.alloc((size_t)h->B * 48);
+    k_pack_summary<<<(unsigned)((h->B + 255) / 256), 256, 0, s>>>(h->Bt, h->r_summary.p);
+    st.launches++;
+  }
+  CK(cudaEventRecord(ev[1], s));
+  CK(cudaStreamSynchronize(s));
+  if (have_prev) {
+    float a = 0;
+    CK(cudaEventElapsedTime(&a, ev[3], ev[4])); t_jac += a;
+    CK(cudaEventElapsedTime(&a, ev[4], ev[5])); t_fac += a;
+    CK(cudaEventElapsedTime(&a, ev[5], ev[6])); t_sol += a;
+    CK(cudaEventElapsedTime(&a, ev[6], ev[7])); t_oth += a;
+  }
+  float tot = 0;
+  CK(cudaEventElapsedTime(&tot, ev[0], ev[1]));
+  st.total_ms = tot; st.mismatch_ms = t_mis; st.jacobian_ms = t_jac; st.factor_ms = t_fac; st.solve_ms = t_sol; st.other_ms = t_oth;
+  st.scenarios_solved = nq;
+  h->ran = true;
+}
+
+static void fetch_results(sblx_handle* h, sblx_results* res) {
+  if (!h->ran) throw std::invalid_argument("sblx_fetch_results: no completed run");
+  const double t0 = now_ms();
+  const int64_t B = h->B;
+  const int n = h->H.n;
+  cudaStream_t s = h->stream;
+  std::vector<int> conv(B), status(B), iter(B), nsw(B);
+  CK(cudaMemcpyAsync(conv.data(), h->r_conv.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(status.data(), h->r_status.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(iter.data(), h->r_iter.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(nsw.data(), h->r_nsw.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  int64_t bytes = 4 * B * sizeof(int);
+  if (res->final_mismatch) { CK(cudaMemcpyAsync(res->final_mismatch, h->r_fm.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
+  if (res->vmin_pu) { CK(cudaMemcpyAsync(res->vmin_pu, h->r_vmin.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
+  if (res->vmax_pu) { CK(cudaMemcpyAsync(res->vmax_pu, h->r_vmax.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
+  if (res->max_loading_pct) { CK(cudaMemcpyAsync(res->max_loading_pct, h->r_load.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
+  if (res->V && h->r_V.p) { CK(cudaMemcpyAsync(res->V, h->r_V.p, (size_t)B * n * 16, cudaMemcpyDeviceToHost, s)); bytes += B * n * 16; }
+  if (res->bus_type_final && h->r_types.p) { CK(cudaMemcpyAsync(res->bus_type_final, h->r_types.p, (size_t)B * n, cudaMemcpyDeviceToHost, s)); bytes += B * n; }
+  CK(cudaStreamSynchronize(s));
+  const HostResults& R = h->hostres;
+  const double nan = std::nan("");
+  for (int64_t k = 0; k < B; ++k) {
+    const bool host = R.status[k] >= 0;
+    if (res->converged) res->converged[k] = host ? 0 : (uint8_t)conv[k];
+    if (res->status) res->status[k] = host ? R.status[k] : status[k];
+    if (res->iterations) res->iterations[k] = host ? 0 : iter[k];
+    if (res->n_switch_events) res->n_switch_events[k] = host ? 0 : nsw[k];
+    if (res->island_count) res->island_count[k] = R.islands[k];
+    if (host) {
+      if (res->final_mismatch) res->final_mismatch[k] = nan;
+      if (res->vmin_pu) res->vmin_pu[k] = nan;
+      if (res->vmax_pu) res->vmax_pu[k] = nan;
+      if (res->max_loading_pct) res->max_loading_pct[k] = nan;
+    }
+  }
+  h->stats.d2h_ms = now_ms() - t0;
+  h->stats.d2h_bytes = bytes;
+}
+
+}  // namespace sblx
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+#define API_BEGIN(h) \
+  try {              \
+    std::lock_guard<std::mutex> lk_((h)->mu);
+#define API_END(h)                                                                    \
+  return SBLX_OK;                                                                     \
+  }                                                                                   \
+  catch (const CudaError& e) { (h)->err = e.what(); return SBLX_E_CUDA; }             \
+  catch (const std::invalid_argument& e) { (h)->err = e.what(); return SBLX_E_ARG; }  \
+  catch (const std::bad_alloc&) { (h)->err = "out of host memory"; return SBLX_E_NOMEM; } \
+  catch (const std::exception& e) { (h)->err = e.what(); return SBLX_E_INTERNAL; }
+
+extern "C" {
+
+int sblx_version(void) { return SBLX_VERSION; }
+
+void sblx_default_options(sblx_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->struct_size = (int32_t)sizeof(sblx_options);
+  o->index_base = 1;
+  o->max_iter = 30;
+  o->qlimits_enabled = 1;
+  o->qlimit_start_iter = 2;
+  o->cooldown_iters = 0;
+  o->guard_max_switches = 10;
+  o->freeze_after_repeated_switching = 1;
+  o->device = -1;
+  o->max_slots = 0;
+  o->ordering = 0;
+  o->tol = 1e-8;
+  o->damp = 1.0;
+  o->q_hyst_pu = 0.0;
+  o->vm_min_pu = 0.9;
+  o->vm_max_pu = 1.1;
+  o->base_mva = 100.0;
+  o->mem_fraction = 0.6;
+  o->relax_zero_frac = 0.08;
+}
+
+const char* sblx_last_error(const sblx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static void fill_host_model(HostModel& H, const sblx_options& o, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                            const double* nzval, int64_t slack_idx, int64_t nbranch, const int32_t* br_from,
+                            const int32_t* br_to) {
+  if (n < 2) throw std::invalid_argument("sblx_create: need at least 2 buses");
+  if (!colptr || !rowval) throw std::invalid_argument("sblx_create: Ybus pattern missing");
+  const int base = o.index_base;
+  if (base != 0 && base != 1) throw std::invalid_argument("sblx_create: index_base must be 0 or 1");
+  H.n = (int)n;
+  H.slack = (int)(slack_idx - base);
+  if (H.slack < 0 || H.slack >= n) throw std::invalid_argument("sblx_create: slack_idx out of range");
+  H.nbr = (int)nbranch;
+  build_pattern(H, n, colptr, rowval, nzval, base, br_from, br_to, nbranch);
+  build_nodes_and_symbolic(H, o);
+}
+
+int sblx_create(sblx_handle** out, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                int64_t slack_idx, const uint8_t* bus_type, const double* vset, const double* s_spec, const double* v0,
+                const double* qmin_pu, const double* qmax_pu, const double* qload_pu, int64_t nbranch,
+                const int32_t* br_from, const int32_t* br_to, const double* br_y11, const double* br_y12,
+                const double* br_y21, const double* br_y22, const double* br_rating, const uint8_t* br_status,
+                const sblx_options* opts) {
+  if (!out) return SBLX_E_ARG;
+  *out = nullptr;
+  sblx_handle* h = nullptr;
+  try {
+    h = new sblx_handle();
+    if (opts) {
+      if (opts->struct_size != (int32_t)sizeof(sblx_options)) throw std::invalid_argument("sblx_create: options struct_size mismatch");
+      h->opt = *opts;
+    } else {
+      sblx_default_options(&h->opt);
+    }
+    if (!nzval || !bus_type || !vset || !s_spec || !v0) throw std::invalid_argument("sblx_create: required array is NULL");
+    if (nbranch > 0 && (!br_from || !br_to || !br_y11 || !br_y12 || !br_y21 || !br_y22))
+      throw std::invalid_argument("sblx_create: branch table incomplete");
+    if (h->opt.max_iter < 1 || !(h->opt.tol > 0) || !(h->opt.damp > 0 && h->opt.damp <= 1.0) || h->opt.qlimit_start_iter < 1)
+      throw std::invalid_argument("sblx_create: invalid solver options");
+    HostModel& H = h->H;
+    fill_host_model(H, h->opt, n, colptr, rowval, nzval, slack_idx, nbranch, br_from, br_to);
+    const int base = h->opt.index_base;
+    H.S0.resize(n); H.V0.resize(n); H.vset.assign(vset, vset + n);
+    H.qmin.resize(n); H.qmax.resize(n); H.qload.resize(n); H.type0.resize(n); H.lockmask.assign(n, 0);
+    int nslack = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      H.S0[i] = make_double2(s_spec[2 * i], s_spec[2 * i + 1]);
+      H.V0[i] = make_double2(v0[2 * i], v0[2 * i + 1]);
+      // limits.jl:211-225: NaN = no limit; the +Inf/-Inf sentinels of buses without generators stay non-finite
+      double lo = qmin_pu ? qmin_pu[i] : -INFINITY, hi = qmax_pu ? qmax_pu[i] : INFINITY;
+      if (std::isnan(lo)) lo = -INFINITY;
+      if (std::isnan(hi)) hi = INFINITY;
+      H.qmin[i] = lo; H.qmax[i] = hi;
+      H.qload[i] = qload_pu ? qload_pu[i] : 0.0;
+      uint8_t t = bus_type[i];
+      if (t > 3) throw std::invalid_argument("sblx_create: unknown bus type");
+      if (t == SBLX_BUS_SLACK) ++nslack;
+      H.type0[i] = t == SBLX_BUS_ISOLATED ? (unsigned char)T_PQ : t;
+    }
+    if (nslack != 1 || bus_type[H.slack] != SBLX_BUS_SLACK)
+      throw std::invalid_argument("sblx_create: exactly one Slack bus at slack_idx is required");
+    H.br_from.resize(nbranch); H.br_to.resize(nbranch); H.y11.resize(nbranch); H.y12.resize(nbranch);
+    H.y21.resize(nbranch); H.y22.resize(nbranch); H.rating.resize(nbranch); H.br_status.resize(nbranch);
+    for (int64_t k = 0; k < nbranch; ++k) {
+      H.br_from[k] = br_from[k] - base; H.br_to[k] = br_to[k] - base;
+      H.y11[k] = make_double2(br_y11[2 * k], br_y11[2 * k + 1]); H.y12[k] = make_double2(br_y12[2 * k], br_y12[2 * k + 1]);
+      H.y21[k] = make_double2(br_y21[2 * k], br_y21[2 * k + 1]); H.y22[k] = make_double2(br_y22[2 * k], br_y22[2 * k + 1]);
+      H.rating[k] = br_rating ? br_rating[k] : std::nan("");
+      H.br_status[k] = br_status ? (br_status[k] != 0) : 1;
+    }
+    build_topology(H);
+    {
+      // islands of the intact grid
+      TopoScratch ts;
+      std::vector<int> iso;
+      int st;
+      H.base_islands = 0;   // force the full analysis
+      H.base_islands = analyze_scenario(H, nullptr, 0, ts, iso, st);
+    }
+    *out = h;
+    return SBLX_OK;
+  } catch (const std::invalid_argument& e) {
+    g_create_error = e.what();
+    delete h;
+    return SBLX_E_ARG;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete h;
+    return SBLX_E_INTERNAL;
+  }
+}
+
+void sblx_destroy(sblx_handle* h) { delete h; }
+
+int sblx_set_locked_pv(sblx_handle* h, int64_t nlock, const int32_t* buses) {
+  if (!h) return SBLX_E_ARG;
+  API_BEGIN(h)
+  std::fill(h->H.lockmask.begin(), h->H.lockmask.end(), 0);
+  for (int64_t k = 0; k < nlock; ++k) {
+    int b = buses[k] - h->opt.index_base;
+    if (b >= 0 && b < h->H.n) h->H.lockmask[b] = 1;
+  }
+  if (h->cuda_ready) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->d_lock.p, h->H.lockmask.data(), h->H.n, cudaMemcpyHostToDevice));
+  }
+  API_END(h)
+}
+
+int sblx_set_v0(sblx_handle* h, const double* v0) {
+  if (!h || !v0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  for (int i = 0; i < h->H.n; ++i) h->H.V0[i] = make_double2(v0[2 * i], v0[2 * i + 1]);
+  if (h->cuda_ready) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->d_V0.p, h->H.V0.data(), (size_t)h->H.n * 16, cudaMemcpyHostToDevice));
+  }
+  API_END(h)
+}
+
+static void fill_info(const sblx_handle* h, sblx_info* info) {
+  const HostModel& H = h->H;
+  const Symbolic& S = H.sym;
+  memset(info, 0, sizeof *info);
+  info->n = H.n; info->m = H.m; info->nnz_y = (int64_t)H.y_col.size();
+  info->nnz_j_blocks = (int64_t)H.jb_col.size();
+  info->nnz_j_scalar = 4 * info->nnz_j_blocks;
+  info->nnz_lu_scalar = S.nnzLU_scalar;
+  info->n_panels = (int64_t)S.panels.size(); info->n_levels = S.nlevels;
+  info->u_blocks = S.u_blocks; info->c_blocks = S.c_blocks;
+  info->max_slots = h->W; info->bytes_per_slot = (int64_t)slot_bytes(H);
+  info->block_ops = S.block_ops;
+  info->algorithmic_bytes_per_iteration = 16.0 * info->nnz_j_scalar + 16.0 * info->nnz_lu_scalar + 128.0 * H.n;
+  snprintf(info->ordering, sizeof info->ordering, "%s", S.ordering_name.c_str());
+}
+
+int sblx_get_info(const sblx_handle* h, sblx_info* info) {
+  if (!h || !info) return SBLX_E_ARG;
+  fill_info(h, info);
+  return SBLX_OK;
+}
+
+int sblx_get_stats(const sblx_handle* h, sblx_stats* s) {
+  if (!h || !s) return SBLX_E_ARG;
+  *s = h->stats;
+  return SBLX_OK;
+}
+
+int sblx_stage_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch, int want_v, int want_types) {
+  if (!h || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (B > 0 && !outage_ptr) throw std::invalid_argument("sblx_stage_outages: outage_ptr is NULL");
+  stage_outages(h, B, outage_ptr, outage_branch, want_v != 0, want_types != 0);
+  API_END(h)
+}
+
+int sblx_run_staged(sblx_handle* h) {
+  if (!h) return SBLX_E_ARG;
+  API_BEGIN(h)
+  run_staged(h);
+  API_END(h)
+}
+
+int sblx_fetch_results(sblx_handle* h, sblx_results* res) {
+  if (!h || !res) return SBLX_E_ARG;
+  API_BEGIN(h)
+  fetch_results(h, res);
+  API_END(h)
+}
+
+int sblx_device_summary(sblx_handle* h, void** dev_ptr, int64_t* nbytes) {
+  if (!h || !dev_ptr || !nbytes) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (!h->ran) throw std::invalid_argument("sblx_device_summary: no completed run");
+  *dev_ptr = h->r_summary.p;
+  *nbytes = h->B * 48;
+  API_END(h)
+}
+
+int sblx_solve_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch, sblx_results* res) {
+  if (!h || !res || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (B == 0) return SBLX_OK;
+  if (!outage_ptr) throw std::invalid_argument("sblx_solve_outages: outage_ptr is NULL");
+  stage_outages(h, B, outage_ptr, outage_branch, res->V != nullptr, res->bus_type_final != nullptr);
+  run_staged(h);
+  fetch_results(h, res);
+  API_END(h)
+}
+
+int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const double* qload_pu, sblx_results* res) {
+  if (!h || !res || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (B == 0) return SBLX_OK;
+  if (!s_spec) throw std::invalid_argument("sblx_solve_injections: s_spec is NULL");
+  stage_outages(h, B, nullptr, nullptr, res->V != nullptr, res->bus_type_final != nullptr);
+  const size_t cnt = (size_t)B * h->H.n;
+  const double t0 = now_ms();
+  h->b_S.alloc(cnt);
+  CK(cudaMemcpyAsync(h->b_S.p, s_spec, cnt * 16, cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes += (int64_t)cnt * 16;
+  if (qload_pu) {
+    h->b_ql.alloc(cnt);
+    CK(cudaMemcpyAsync(h->b_ql.p, qload_pu, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)cnt * 8;
+    h->sweep_q = true;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.h2d_ms += now_ms() - t0;
+  set_batch(h);
+  run_staged(h);
+  fetch_results(h, res);
+  API_END(h)
+}
+
+int sblx_solve_one(sblx_handle* h, const double* v_start, double* v_out, uint8_t* converged, int32_t* iters,
+                   double* residual_inf, int32_t* status) {
+  if (!h) return SBLX_E_ARG;
+  API_BEGIN(h)
+  int32_t optr[2] = {0, 0};
+  stage_outages(h, 1, optr, nullptr, v_out != nullptr, false);
+  if (v_start) {
+    std::vector<double2> vs(h->H.n);
+    for (int i = 0; i < h->H.n; ++i) vs[i] = make_double2(v_start[2 * i], v_start[2 * i + 1]);
+    h->b_Vstart.upload(vs, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    set_batch(h);
+  }
+  run_staged(h);
+  sblx_results r{};
+  uint8_t c = 0;
+  int32_t it = 0, stt = 0;
+  double fm = 0;
+  r.converged = &c; r.iterations = &it; r.status = &stt; r.final_mismatch = &fm; r.V = v_out;
+  fetch_results(h, &r);
+  if (converged) *converged = c;
+  if (iters) *iters = it;
+  if (residual_inf) *residual_inf = fm;
+  if (status) *status = stt;
+  API_END(h)
+}
+
+int sblx_debug_pattern(const sblx_handle* h, int64_t* rowptr, int32_t* col) {
+  if (!h) return SBLX_E_ARG;
+  const HostModel& H = h->H;
+  if (rowptr) for (int a = 0; a <= H.m; ++a) rowptr[a] = H.jb_rowptr[a];
+  if (col) for (size_t k = 0; k < H.jb_col.size(); ++k) col[k] = H.bus_of_node[H.jb_col[k]];
+  return SBLX_OK;
+}
+
+int sblx_debug_newton_step(sblx_handle* h, int64_t nout, const int32_t* outage_branch, const uint8_t* bus_type,
+                           const double* v_in, double* F, double* jblocks, double* dx, double* max_mismatch) {
+  if (!h || !v_in) return SBLX_E_ARG;
+  API_BEGIN(h)
+  const HostModel& H = h->H;
+  const int n = H.n, m = H.m, nnzB = (int)H.jb_col.size();
+  int32_t optr[2] = {0, (int32_t)nout};
+  stage_outages(h, 1, optr, outage_branch, false, false);
+  if (h->nq != 1) throw std::invalid_argument("sblx_debug_newton_step: scenario is islanded / invalid");
+  std::vector<double2> vs(n);
+  for (int i = 0; i < n; ++i) vs[i] = make_double2(v_in[2 * i], v_in[2 * i + 1]);
+  h->b_Vstart.upload(vs, h->stream);
+  set_batch(h);
+  cudaStream_t s = h->stream;
+  CK(cudaMemsetAsync(h->s_state.p, 0, h->W * sizeof(int), s));
+  CK(cudaMemsetAsync(h->s_scen.p, 0xff, h->W * sizeof(int), s));
+  CK(cudaMemsetAsync(h->l_counts.p, 0, 8 * sizeof(int), s));
+  k_assign<<<1, 1024, 0, s>>>(h->M, h->A, h->L, h->Bt);
+  k_init<<<dim3((n + 7) / 8, 1), dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
+  k_init_iso<<<1, 128, 0, s>>>(h->M, h->A, h->L, h->Bt);
+  if (bus_type) {
+    // override the active set of slot 0 (interleaved stride W)
+    std::vector<unsigned char> t(n);
+    for (int i = 0; i < n; ++i) t[i] = bus_type[i] == SBLX_BUS_ISOLATED ? (unsigned char)T_PQ : bus_type[i];
+    CK(cudaMemcpy2DAsync(h->s_type.p, h->W, t.data(), 1, 1, n, cudaMemcpyHostToDevice, s));
+  }
+  k_mismatch<<<dim3((n + 7) / 8, 1), dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+  // force a step list of {slot 0}
+  int one[8] = {1, 0, 1, 0, 1, 0, 0, 0};
+  int zero = 0;
+  CK(cudaMemcpyAsync(h->l_counts.p, one, sizeof one, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->l_step.p, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
+  k_jacobian<<<dim3((nnzB + 7) / 8, 1), dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+  for (size_t l = 0; l < h->front_groups.size(); ++l)
+    for (const LaunchGroup& g : h->front_groups[l]) {
+      switch (g.nt) {
+        case 32: launch_front<32>(h, g, 1); break;
+        case 64: launch_front<64>(h, g, 1); break;
+        case 128: launch_front<128>(h, g, 1); break;
+        default: launch_front<256>(h, g, 1); break;
+      }
+    }
+  for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
+    for (const LaunchGroup& g : h->solve_groups[l]) {
+      switch (g.nt) {
+        case 32: launch_solve<32>(h, g, 1); break;
+        case 64: launch_solve<64>(h, g, 1); break;
+        default: launch_solve<128>(h, g, 1); break;
+      }
+    }
+  CK(cudaGetLastError());
+  std::vector<double2> rhs(m), xv(m);
+  std::vector<double> J((size_t)nnzB * 4);
+  unsigned long long mb = 0;
+  CK(cudaMemcpyAsync(rhs.data(), h->s_rhs.p, m * 16, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(xv.data(), h->s_xv.p, m * 16, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(J.data(), h->s_Jv.p, (size_t)nnzB * 32, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&mb, h->s_mis.p, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const Symbolic& S = H.sym;
+  for (int a = 0; a < m; ++a) {
+    const int e = S.iperm[a];
+    if (F) { F[2 * a] = -rhs[e].x; F[2 * a + 1] = -rhs[e].y; }
+    if (dx) { dx[2 * a] = xv[e].x; dx[2 * a + 1] = xv[e].y; }
+  }
+  if (jblocks) memcpy(jblocks, J.data(), J.size() * sizeof(double));
+  if (max_mismatch) memcpy(max_mismatch, &mb, 8);
+  h->staged = false;
+  API_END(h)
+}
+
+int sblx_debug_host_selftest(const sblx_handle* h, uint64_t seed, double* rel_residual) {
+  if (!h || !rel_residual) return SBLX_E_ARG;
+  try {
+    *rel_residual = host_selftest(h->H, seed);
+    return SBLX_OK;
+  } catch (const std::exception&) {
+    return SBLX_E_INTERNAL;
+  }
+}
+
+int sblx_analyze_only(int64_t n, const int64_t* colptr, const int64_t* rowval, int64_t slack_idx, const sblx_options* opts,
+                      sblx_info* info, double* selftest_residual) {
+  try {
+    sblx_handle h;
+    if (opts) h.opt = *opts; else sblx_default_options(&h.opt);
+    fill_host_model(h.H, h.opt, n, colptr, rowval, nullptr, slack_idx, 0, nullptr, nullptr);
+    if (info) fill_info(&h, info);
+    if (selftest_residual) *selftest_residual = host_selftest(h.H, 12345);
+    return SBLX_OK;
+  } catch (const std::invalid_argument& e) {
+    g_create_error = e.what();
+    return SBLX_E_ARG;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return SBLX_E_INTERNAL;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,873 @@
+// sm_100a CUDA kernels of the batched rectangular Newton-Raphson engine.
+//
+// Layout in HBM (W = resident scenario slots):
+//   * per-bus state is SCENARIO-INTERLEAVED  [bus][slot]  (V, I, S, type, Q-limit bookkeeping):
+//     a warp = 32 scenarios of the same bus, so the shared Ybus pattern/value loads are warp
+//     broadcasts and every state load/store is a fully coalesced 512 B (double2) access;
+//   * everything the factorisation touches is SCENARIO-MAJOR  [slot][entry]  (rhs, Jacobian 2x2
+//     blocks, stored U panels, update-matrix arena, y, x): one CTA factors one front of one
+//     scenario and streams contiguous 32 B blocks.
+// Reference semantics restated per kernel (paths relative to Sparlectra.jl/src):
+//   k_mismatch  - calc_injections + mismatch_rectangular        solver_core.jl:35-47,
+//                                                               powerflow_rectangular/rectangular_core_equations.jl:79-148
+//   k_qlimit    - _handle_rectangular_qlimit_iteration! + active_set_q_limits!
+//                                                               powerflow_rectangular/rectangular_qlimit_iteration.jl:25-210, limits.jl:398-568
+//   k_decide    - NR loop control                               powerflow_rectangular/rectangular_network_solver.jl:746-852
+//   k_jacobian  - _assemble_rectangular_jacobian!               powerflow_rectangular/rectangular_jacobian_builders.jl:212-429
+//   k_front / k_backsolve - solve_linear(J, -F) (UMFPACK there) solver_core.jl:60-111
+//   k_update    - _apply_rectangular_delta! + slack reset       powerflow_rectangular/rectangular_newton_step.jl:38-55, rectangular_network_solver.jl:919
+//   k_fin_*     - final acceptance + contingency metrics        rectangular_network_solver.jl:939-1094, contingency.jl:149-178, losses.jl:53-85
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sblx {
+
+constexpr int MAXOUT = 8;          // outaged branches per scenario (N-k, k <= 8)
+constexpr int ST_IDLE = 0, ST_RUN = 1, ST_DRAIN = 2;
+constexpr int T_ISO = 0, T_PQ = 1, T_PV = 2, T_SLACK = 3;
+
+struct PanelDev {
+  int first, w, h, nchild;
+  int struct_ptr, child_ptr, asm_ptr, asm_cnt;
+  long long u_off, c_off;
+};
+
+struct DevModel {
+  int n, m, slack, nbr, nnzB, W;
+  const int* y_rowptr; const int* y_col; const double2* y_val;
+  const int* node_of_bus; const int* bus_of_node; const int* elim_of_node; const int* node_of_elim;
+  const int* jb_row; const int* jb_col; const int* jb_ypos;
+  const double2* S0; const double2* V0; const double* vset; const double* qmin; const double* qmax;
+  const double* qload; const unsigned char* type0; const unsigned char* lockmask;
+  const int* br_from; const int* br_to; const double2* y11; const double2* y12; const double2* y21; const double2* y22;
+  const double* rating; const unsigned char* br_status;
+  const PanelDev* panels; const int* struct_nodes; const int* child_list; const int* rel; const long long* rel_ptr;
+  const int* kpiv; const int* inv; const long long* inv_ptr; const int* asm_src; const int* asm_dst;
+  long long u_blocks, c_blocks;
+  double tol, damp, hyst, vm_min, vm_max, base_mva;
+  int max_iter, qlim_enabled, qlim_start, cooldown, guard, freeze, allow_reenable;
+};
+
+struct Slots {
+  // [n][W]
+  double2* V; double2* I; double2* S; double* qload_s;
+  unsigned char* type; unsigned char* iso; unsigned char* evcnt; unsigned char* evact; short* evlast;
+  // [W][...]
+  double2* rhs; double* Jv; double* U; double* C; double2* yv; double2* xv;
+  // [W]
+  int* scen; int* iter; int* state; int* changed; int* nev; int* singular; int* numerical; int* reason;
+  unsigned long long* mis_bits; unsigned long long* mis2_bits; double* fm;
+  unsigned long long* pvres_bits; unsigned long long* vmin_bits; unsigned long long* vmax_bits; unsigned long long* load_bits;
+  int* viol; int* maxsw; int* rated;
+  int* out_cnt; int* out_br;   // [W][MAXOUT]
+};
+
+struct Lists {
+  int* active; int* fresh; int* step; int* fin;
+  int* counts;   // [0] nActive [1] nFresh [2] nStep [3] nFin [4] queue head [5] nDrain
+};
+
+struct Batch {
+  int B, nq, use_sweep_q;
+  const int* queue; const int* out_ptr; const int* out_br; const int* iso_ptr; const int* iso_bus;
+  const double2* Ssweep; const double* qlsweep; const double2* Vstart;
+  // results
+  int* r_conv; int* r_status; int* r_iter; int* r_nsw; double* r_fm; double* r_vmin; double* r_vmax; double* r_load;
+  double2* r_V; unsigned char* r_types;
+};
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ unsigned long long abs_bits(double x) { return (unsigned long long)__double_as_longlong(fabs(x)); }
+__device__ __forceinline__ double bits_double(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+// exclusive scan of 0/1 flags over a block of 1024 threads; returns rank, writes block total
+__device__ __forceinline__ int block_rank_1024(int flag, int* total) {
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned b = __ballot_sync(0xffffffffu, flag);
+  int r = __popc(b & ((1u << lane) - 1u));
+  if (lane == 0) wsum[warp] = __popc(b);
+  __syncthreads();
+  if (warp == 0) {
+    int v = wsum[lane];
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    wsum[lane] = s - v;            // exclusive
+    if (lane == 31) *total = s;
+  }
+  __syncthreads();
+  r += wsum[warp];
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// tick bookkeeping: assign pending scenarios to idle slots, build active / drain lists
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_assign(DevModel M, Slots A, Lists L, Batch Bt) {
+  __shared__ int s_total;
+  __shared__ int s_qhead, s_nfresh, s_nact, s_ndrain;
+  if (threadIdx.x == 0) { s_qhead = L.counts[4]; s_nfresh = 0; s_nact = 0; s_ndrain = 0; }
+  __syncthreads();
+  for (int base = 0; base < M.W; base += 1024) {
+    const int slot = base + threadIdx.x;
+    const bool valid = slot < M.W;
+    int st = valid ? A.state[slot] : -1;
+    int idle = (st == ST_IDLE);
+    int rank = block_rank_1024(idle, &s_total);
+    int qh = s_qhead, nf = s_nfresh;
+    if (idle) {
+      int q = qh + rank;
+      if (q < Bt.nq) {
+        A.scen[slot] = Bt.queue[q];
+        A.state[slot] = ST_RUN;
+        A.iter[slot] = 0;
+        L.fresh[nf + rank] = slot;
+        st = ST_RUN;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int take = min(s_total, max(Bt.nq - qh, 0));
+      s_qhead = qh + take;
+      s_nfresh = nf + take;
+    }
+    __syncthreads();
+    int run = (st == ST_RUN);
+    int r2 = block_rank_1024(run, &s_total);
+    int na = s_nact;
+    if (run) {
+      L.active[na + r2] = slot;
+      A.mis_bits[slot] = 0ull;
+      A.mis2_bits[slot] = 0ull;
+      A.changed[slot] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_nact = na + s_total;
+    __syncthreads();
+    int dr = (st == ST_DRAIN);
+    int r3 = block_rank_1024(dr, &s_total);
+    int nd = s_ndrain;
+    if (dr) L.fin[nd + r3] = slot;
+    __syncthreads();
+    if (threadIdx.x == 0) s_ndrain = nd + s_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    L.counts[0] = s_nact;
+    L.counts[1] = s_nfresh;
+    L.counts[4] = s_qhead;
+    L.counts[5] = s_ndrain;
+  }
+}
+
+// grid (ceil(n/8), ceil(nFresh/32)), block (32, 8)
+__global__ void __launch_bounds__(256) k_init(DevModel M, Slots A, Lists L, Batch Bt) {
+  const int nf = L.counts[1];
+  const int li = blockIdx.y * 32 + threadIdx.x;
+  const int bus = blockIdx.x * 8 + threadIdx.y;
+  if (li >= nf || bus >= M.n) return;
+  const int slot = L.fresh[li];
+  const int scen = A.scen[slot];
+  const size_t k = (size_t)bus * M.W + slot;
+  A.V[k] = Bt.Vstart ? Bt.Vstart[bus] : M.V0[bus];
+  A.S[k] = Bt.Ssweep ? Bt.Ssweep[(size_t)scen * M.n + bus] : M.S0[bus];
+  if (A.qload_s) A.qload_s[k] = Bt.qlsweep ? Bt.qlsweep[(size_t)scen * M.n + bus] : M.qload[bus];
+  A.type[k] = M.type0[bus];
+  A.iso[k] = 0;
+  A.evcnt[k] = 0;
+  A.evact[k] = 0;
+  A.evlast[k] = 0;
+  A.I[k] = make_double2(0.0, 0.0);
+  if (bus == 0) {
+    A.nev[slot] = 0;
+    A.singular[slot] = 0;
+    A.numerical[slot] = 0;
+    A.reason[slot] = 1;
+    A.fm[slot] = 0.0;
+    int cnt = 0;
+    if (Bt.out_ptr) {
+      int b = Bt.out_ptr[scen], e = Bt.out_ptr[scen + 1];
+      for (int q = b; q < e && cnt < MAXOUT; ++q) {
+        int br = Bt.out_br[q];
+        if (br >= 0 && br < M.nbr && M.br_status[br]) A.out_br[slot * MAXOUT + cnt++] = br;
+      }
+    }
+    A.out_cnt[slot] = cnt;
+  }
+}
+
+// isolated buses of the freshly assigned scenarios (host-detected: markIsolatedBuses!,
+// network.jl:1881-1930): neutral PQ rows with S = 0, V = 1 (rectangular_network_solver.jl:508-512,
+// network.jl:2318 `vm <= 0 => 1.0`).  grid ceil(nFresh/128)
+__global__ void k_init_iso(DevModel M, Slots A, Lists L, Batch Bt) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= L.counts[1] || !Bt.iso_ptr) return;
+  const int slot = L.fresh[li];
+  const int scen = A.scen[slot];
+  for (int q = Bt.iso_ptr[scen]; q < Bt.iso_ptr[scen + 1]; ++q) {
+    const int bus = Bt.iso_bus[q];
+    const size_t k = (size_t)bus * M.W + slot;
+    A.iso[k] = 1;
+    A.type[k] = T_PQ;
+    A.S[k] = make_double2(0.0, 0.0);
+    A.V[k] = make_double2(1.0, 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: I = Ybus(s) V, S_calc = V conj(I), rhs = -F, per-scenario max |F|
+// grid (ceil(n/8), ceil(nActive/32)), block (32, 8): lane = scenario, ty = bus
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 residual_rows(int type, double2 V, double2 Sc, double2 S, double vset) {
+  // F = calc - spec ; PV second row is |V| - Vset (rectangular_core_equations.jl:116-128)
+  double f0 = Sc.x - S.x;
+  double f1 = (type == T_PV) ? (sqrt(V.x * V.x + V.y * V.y) - vset) : (Sc.y - S.y);
+  return make_double2(f0, f1);
+}
+
+__global__ void __launch_bounds__(256) k_mismatch(DevModel M, Slots A, Lists L) {
+  __shared__ unsigned long long smax[8][32];
+  const int na = L.counts[0];
+  const int li = blockIdx.y * 32 + threadIdx.x;
+  const int bus = blockIdx.x * 8 + threadIdx.y;
+  unsigned long long mybits = 0ull;
+  int slot = -1;
+  if (li < na && bus < M.n) {
+    slot = L.active[li];
+    const size_t W = M.W;
+    const size_t k = (size_t)bus * W + slot;
+    double2 I = make_double2(0.0, 0.0);
+    const double2 Vi = A.V[k];
+    if (!A.iso[k]) {
+      for (int p = M.y_rowptr[bus]; p < M.y_rowptr[bus + 1]; ++p) {
+        const double2 y = M.y_val[p];
+        const double2 v = A.V[(size_t)M.y_col[p] * W + slot];
+        I.x += y.x * v.x - y.y * v.y;
+        I.y += y.x * v.y + y.y * v.x;
+      }
+      const int no = A.out_cnt[slot];
+      for (int o = 0; o < no; ++o) {
+        const int br = A.out_br[slot * MAXOUT + o];
+        const int f = M.br_from[br], t = M.br_to[br];
+        if (bus == f) {
+          I = csub(I, cadd(cmul(M.y11[br], Vi), cmul(M.y12[br], A.V[(size_t)t * W + slot])));
+        } else if (bus == t) {
+          I = csub(I, cadd(cmul(M.y22[br], Vi), cmul(M.y21[br], A.V[(size_t)f * W + slot])));
+        }
+      }
+    }
+    A.I[k] = I;
+    if (bus != M.slack) {
+      const double2 Sc = cmul(Vi, cconj(I));
+      const double2 F = residual_rows(A.type[k], Vi, Sc, A.S[k], M.vset[bus]);
+      const int e = M.elim_of_node[M.node_of_bus[bus]];
+      A.rhs[(size_t)slot * M.m + e] = make_double2(-F.x, -F.y);
+      unsigned long long b0 = abs_bits(F.x), b1 = abs_bits(F.y);
+      mybits = b0 > b1 ? b0 : b1;
+    }
+  }
+  smax[threadIdx.y][threadIdx.x] = mybits;
+  __syncthreads();
+  if (threadIdx.y == 0 && slot >= 0) {
+    unsigned long long v = smax[0][threadIdx.x];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+      unsigned long long t = smax[r][threadIdx.x];
+      v = t > v ? t : v;
+    }
+    atomicMax(&A.mis_bits[slot], v);   // NaN bit patterns sort above +Inf: NaN-propagating max
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: Q-limit active set. Same mapping as k_mismatch.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_qlimit(DevModel M, Slots A, Lists L) {
+  const int na = L.counts[0];
+  const int li = blockIdx.y * 32 + threadIdx.x;
+  const int bus = blockIdx.x * 8 + threadIdx.y;
+  if (li >= na || bus >= M.n || bus == M.slack) return;
+  const int slot = L.active[li];
+  const size_t k = (size_t)bus * M.W + slot;
+  const int type0 = M.type0[bus];
+  if (type0 != T_PV || A.iso[k]) return;       // only originally-PV buses ever take part
+  const double mis = bits_double(A.mis_bits[slot]);
+  const int it = A.iter[slot] + 1;
+  const bool conv_now = mis <= M.tol;           // false for NaN
+  const bool ready = (it >= M.qlim_start) || conv_now;   // rectangular_qlimit_iteration.jl:86,111
+  if (!ready) return;
+  const double qmin = M.qmin[bus], qmax = M.qmax[bus];
+  const bool has_lo = isfinite(qmin), has_hi = isfinite(qmax);
+  if (!(has_lo || has_hi)) return;
+  int type = A.type[k];
+  const double2 Vi = A.V[k];
+  const double2 Sc = cmul(Vi, cconj(A.I[k]));
+  const double ql = A.qload_s ? A.qload_s[k] : M.qload[bus];
+  const double qreq = Sc.y + ql;
+  bool touched = false;
+  if (type == T_PV && !M.lockmask[bus]) {
+    int side = 0;
+    double clamp = 0.0;
+    if (has_hi && qreq > qmax + M.hyst) { side = 1; clamp = qmax; }
+    else if (has_lo && qreq < qmin - M.hyst) { side = -1; clamp = qmin; }
+    if (side != 0 && !(M.freeze && A.evcnt[k] >= M.guard)) {
+      type = T_PQ;                                          // make_pq! (rectangular_qlimit_iteration.jl:178-183)
+      A.type[k] = T_PQ;
+      double2 S = A.S[k];
+      S.y = clamp - ql;
+      A.S[k] = S;
+      A.evcnt[k] = (unsigned char)min(255, A.evcnt[k] + 1);   // logQLimitHit!
+      A.evact[k] = 1;
+      A.evlast[k] = (short)it;
+      atomicAdd(&A.nev[slot], 1);
+      atomicOr(&A.changed[slot], 1);
+      touched = true;
+    }
+  }
+  if (M.allow_reenable && type != T_PV && A.evact[k] && A.evcnt[k] <= 1) {    // limits.jl:527-561
+    const double lo = has_lo ? qmin + M.hyst : -INFINITY;
+    const double hi = has_hi ? qmax - M.hyst : INFINITY;
+    bool rdy = (qreq > lo) && (qreq < hi);
+    if (rdy && M.cooldown > 0 && (it - (int)A.evlast[k]) < M.cooldown) rdy = false;
+    if (rdy) {
+      type = T_PV;
+      A.type[k] = T_PV;
+      A.evact[k] = 0;
+      atomicOr(&A.changed[slot], 2);
+      touched = true;
+    }
+  }
+  if (touched) {
+    const double2 F = residual_rows(type, Vi, Sc, A.S[k], M.vset[bus]);
+    const int e = M.elim_of_node[M.node_of_bus[bus]];
+    A.rhs[(size_t)slot * M.m + e] = make_double2(-F.x, -F.y);
+  }
+}
+
+// mismatch norm after an active-set change (history[end] = max_mis, rectangular_qlimit_iteration.jl:195-204)
+// grid nActive, block 256
+__global__ void __launch_bounds__(256) k_norm(DevModel M, Slots A, Lists L) {
+  __shared__ unsigned long long red[256];
+  if ((int)blockIdx.x >= L.counts[0]) return;
+  const int slot = L.active[blockIdx.x];
+  if (!A.changed[slot]) return;
+  const double2* r = A.rhs + (size_t)slot * M.m;
+  unsigned long long v = 0ull;
+  for (int e = threadIdx.x; e < M.m; e += 256) {
+    double2 x = r[e];
+    unsigned long long a = abs_bits(x.x), b = abs_bits(x.y);
+    a = a > b ? a : b;
+    v = a > v ? a : v;
+  }
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      unsigned long long t = red[threadIdx.x + s];
+      if (t > red[threadIdx.x]) red[threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) A.mis2_bits[slot] = red[0];
+}
+
+// NR loop control (rectangular_network_solver.jl:746-852). single block of 1024 threads.
+__global__ void __launch_bounds__(1024) k_decide(DevModel M, Slots A, Lists L) {
+  __shared__ int s_total, s_nstep, s_nfin;
+  const int na = L.counts[0];
+  if (threadIdx.x == 0) { s_nstep = 0; s_nfin = L.counts[5]; }
+  __syncthreads();
+  for (int base = 0; base < na; base += 1024) {
+    const int li = base + threadIdx.x;
+    int step = 0, fin = 0, slot = -1;
+    if (li < na) {
+      slot = L.active[li];
+      const int it = A.iter[slot] + 1;
+      A.iter[slot] = it;
+      const double mis = bits_double(A.mis_bits[slot]);
+      const int ch = A.changed[slot];
+      A.fm[slot] = ch ? bits_double(A.mis2_bits[slot]) : mis;
+      if (!isfinite(mis)) {
+        A.numerical[slot] = 0; A.reason[slot] = 2; fin = 1;      // :nr_nonfinite
+      } else if (mis <= M.tol && !ch) {
+        A.numerical[slot] = 1; A.reason[slot] = 0; fin = 1;      // converged, active set stable
+      } else {
+        step = 1;
+      }
+    }
+    int r = block_rank_1024(step, &s_total);
+    int ns = s_nstep;
+    if (step) L.step[ns + r] = slot;
+    __syncthreads();
+    if (threadIdx.x == 0) s_nstep = ns + s_total;
+    __syncthreads();
+    int r2 = block_rank_1024(fin, &s_total);
+    int nf = s_nfin;
+    if (fin) L.fin[nf + r2] = slot;
+    __syncthreads();
+    if (threadIdx.x == 0) s_nfin = nf + s_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { L.counts[2] = s_nstep; L.counts[3] = s_nfin; }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: Jacobian 2x2 blocks into the fixed superset pattern.
+// grid (ceil(nnzB/8), ceil(nStep/32)), block (32, 8): lane = scenario, ty = block entry
+// block = [dP/dVr dP/dVi ; dQ/dVr dQ/dVi]  (PV: second row = d|V|/dVr, d|V|/dVi on the diagonal)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_jacobian(DevModel M, Slots A, Lists L) {
+  const int ns = L.counts[2];
+  const int li = blockIdx.y * 32 + threadIdx.x;
+  const int ent = blockIdx.x * 8 + threadIdx.y;
+  if (li >= ns || ent >= M.nnzB) return;
+  const int slot = L.step[li];
+  const size_t W = M.W;
+  const int i = M.bus_of_node[M.jb_row[ent]], j = M.bus_of_node[M.jb_col[ent]];
+  const size_t ki = (size_t)i * W + slot;
+  double b00 = 0, b01 = 0, b10 = 0, b11 = 0;
+  const bool isoi = A.iso[ki] != 0, isoj = A.iso[(size_t)j * W + slot] != 0;
+  if (isoi || isoj) {
+    if (i == j) { b00 = 1.0; b11 = 1.0; }              // neutral identity row/col: delta = 0
+  } else {
+    double2 y = M.y_val[M.jb_ypos[ent]];
+    const int no = A.out_cnt[slot];
+    for (int o = 0; o < no; ++o) {
+      const int br = A.out_br[slot * MAXOUT + o];
+      const int f = M.br_from[br], t = M.br_to[br];
+      if (i == j) {
+        if (i == f) y = csub(y, M.y11[br]);
+        else if (i == t) y = csub(y, M.y22[br]);
+      } else if (i == f && j == t) y = csub(y, M.y12[br]);
+      else if (i == t && j == f) y = csub(y, M.y21[br]);
+    }
+    const double2 Vi = A.V[ki];
+    const double2 a = cmul(Vi, cconj(y));        // A = V_i conj(Y_ij)
+    double2 dvr = a;                              // dS/dVr
+    double2 dvi = make_double2(a.y, -a.x);        // dS/dVi = i*(-A)
+    if (i == j) {
+      const double2 I = A.I[ki];
+      dvr.x += I.x; dvr.y -= I.y;                 // + conj(I)
+      dvi.x += I.y; dvi.y += I.x;                 // + i*conj(I)
+    }
+    b00 = dvr.x; b01 = dvi.x;
+    if (A.type[ki] == T_PV) {
+      if (i == j) {
+        const double vm = sqrt(Vi.x * Vi.x + Vi.y * Vi.y);
+        const double d = vm > 0.0 ? vm : 1e-9;    // vm_eps (rectangular_jacobian_builders.jl:362)
+        b10 = Vi.x / d; b11 = Vi.y / d;
+      }
+    } else {
+      b10 = dvr.y; b11 = dvi.y;
+    }
+  }
+  double2* out = reinterpret_cast<double2*>(A.Jv + ((size_t)slot * M.nnzB + ent) * 4);
+  out[0] = make_double2(b00, b01);
+  out[1] = make_double2(b10, b11);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: multifrontal panel factorisation, one CTA per (front, scenario).
+// shared memory (double2 = one block row): T0/T1 [w][nf] pivot rows, L0/L1 [h][w] structure
+// rows x pivot cols, b1 [w] rhs of the pivots.  T rows are stored pre-scaled by the inverse
+// pivot block (U' = D^-1 U, y' = D^-1 y) so the back substitution has no division.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool inv2x2(double2 r0, double2 r1, double2& i0, double2& i1) {
+  // inverse of [[a,b],[c,d]] with the determinant taken through the partially pivoted LU
+  const double a = r0.x, b = r0.y, c = r1.x, d = r1.y;
+  double det;
+  if (fabs(a) >= fabs(c)) det = (a == 0.0) ? 0.0 : a * (d - (c / a) * b);
+  else det = -c * (b - (a / c) * d);
+  const bool ok = isfinite(det) && det != 0.0;
+  const double s = ok ? 1.0 / det : 0.0;
+  i0 = make_double2(d * s, -b * s);
+  i1 = make_double2(-c * s, a * s);
+  return ok;
+}
+// t -= a * u for 2x2 blocks (rows as double2)
+__device__ __forceinline__ void bmsub(double2& t0, double2& t1, double2 a0, double2 a1, double2 u0, double2 u1) {
+  t0.x -= a0.x * u0.x + a0.y * u1.x;
+  t0.y -= a0.x * u0.y + a0.y * u1.y;
+  t1.x -= a1.x * u0.x + a1.y * u1.x;
+  t1.y -= a1.x * u0.y + a1.y * u1.y;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+  extern __shared__ double2 sm2[];
+  const int panel = panel_ids[blockIdx.x];
+  if ((int)blockIdx.y >= L.counts[2]) return;
+  const int slot = L.step[blockIdx.y];
+  const PanelDev P = M.panels[panel];
+  const int w = P.w, h = P.h, nf = w + h;
+  const int tid = threadIdx.x;
+  double2* T0 = sm2;
+  double2* T1 = T0 + w * nf;
+  double2* L0 = T1 + w * nf;
+  double2* L1 = L0 + h * w;
+  double2* b1 = L1 + h * w;
+  const int nT = w * nf, nL = h * w;
+  {
+    const int tot = 2 * nT + 2 * nL + w;
+    for (int i = tid; i < tot; i += NT) sm2[i] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  // ---- original Jacobian blocks of this front
+  {
+    const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
+    for (int k = tid; k < P.asm_cnt; k += NT) {
+      const int src = M.asm_src[P.asm_ptr + k], dst = M.asm_dst[P.asm_ptr + k];
+      const double2 r0 = Jv[2 * src], r1 = Jv[2 * src + 1];
+      if (dst < nT) { T0[dst] = r0; T1[dst] = r1; }
+      else { L0[dst - nT] = r0; L1[dst - nT] = r1; }
+    }
+    const double2* r = A.rhs + (size_t)slot * M.m + P.first;
+    for (int p = tid; p < w; p += NT) b1[p] = r[p];
+  }
+  __syncthreads();
+  double* Cs = A.C + (size_t)slot * M.c_blocks * 4;
+  // ---- extend-add of the children's update matrices into the pivot rows / columns
+  for (int ci = 0; ci < P.nchild; ++ci) {
+    const int c = M.child_list[P.child_ptr + ci];
+    const PanelDev Cp = M.panels[c];
+    const int hc = Cp.h, kc = M.kpiv[c];
+    const int* rel = M.rel + M.rel_ptr[c];
+    const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
+    const double2* cv = Cm + 2 * (size_t)hc * hc;
+    const int n1 = kc * hc, n2 = (hc - kc) * kc;
+    for (int idx = tid; idx < n1 + n2; idx += NT) {
+      int a, b;
+      if (idx < n1) { a = idx / hc; b = idx - a * hc; }
+      else { const int t = idx - n1; a = kc + t / kc; b = t - (a - kc) * kc; }
+      const int la = rel[a], lb = rel[b];
+      const double2 s0 = Cm[2 * (a * hc + b)], s1 = Cm[2 * (a * hc + b) + 1];
+      if (la < w) {
+        const int d = la * nf + lb;
+        T0[d] = cadd(T0[d], s0); T1[d] = cadd(T1[d], s1);
+      } else {
+        const int d = (la - w) * w + lb;
+        L0[d] = cadd(L0[d], s0); L1[d] = cadd(L1[d], s1);
+      }
+    }
+    for (int a = tid; a < kc; a += NT) b1[rel[a]] = cadd(b1[rel[a]], cv[a]);
+    __syncthreads();
+  }
+  // ---- right-looking factorisation of the w pivots inside the panel
+  bool sing = false;
+  for (int p = 0; p < w; ++p) {
+    double2 d0, d1;
+    const bool ok = inv2x2(T0[p * nf + p], T1[p * nf + p], d0, d1);
+    sing |= !ok;          // (the pivot block itself is never rescaled, so no barrier is needed here)
+    for (int c = p + tid; c < nf + 1; c += NT) {
+      if (c == p) continue;
+      if (c == nf) {       // rhs entry
+        const double2 v = b1[p];
+        b1[p] = make_double2(d0.x * v.x + d0.y * v.y, d1.x * v.x + d1.y * v.y);
+      } else {
+        const double2 u0 = T0[p * nf + c], u1 = T1[p * nf + c];
+        T0[p * nf + c] = make_double2(d0.x * u0.x + d0.y * u1.x, d0.x * u0.y + d0.y * u1.y);
+        T1[p * nf + c] = make_double2(d1.x * u0.x + d1.y * u1.x, d1.x * u0.y + d1.y * u1.y);
+      }
+    }
+    __syncthreads();
+    const int nr = w - p - 1, nc = nf - p - 1;
+    const int n1 = nr * nc, n2 = h * nr;
+    for (int idx = tid; idx < n1 + n2 + nr; idx += NT) {
+      if (idx < n1) {
+        const int i = p + 1 + idx / nc, c = p + 1 + idx % nc;
+        bmsub(T0[i * nf + c], T1[i * nf + c], T0[i * nf + p], T1[i * nf + p], T0[p * nf + c], T1[p * nf + c]);
+      } else if (idx < n1 + n2) {
+        const int t = idx - n1;
+        const int a = t / nr, c = p + 1 + t % nr;
+        bmsub(L0[a * w + c], L1[a * w + c], L0[a * w + p], L1[a * w + p], T0[p * nf + c], T1[p * nf + c]);
+      } else {
+        const int i = p + 1 + (idx - n1 - n2);
+        const double2 y = b1[p];
+        const double2 a0 = T0[i * nf + p], a1 = T1[i * nf + p];
+        double2 v = b1[i];
+        v.x -= a0.x * y.x + a0.y * y.y;
+        v.y -= a1.x * y.x + a1.y * y.y;
+        b1[i] = v;
+      }
+    }
+    __syncthreads();
+  }
+  if (sing && tid == 0) atomicOr(&A.singular[slot], 1);
+  // ---- store U' panel and y'
+  {
+    double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
+    for (int i = tid; i < nT; i += NT) { U[2 * i] = T0[i]; U[2 * i + 1] = T1[i]; }
+    double2* y = A.yv + (size_t)slot * M.m + P.first;
+    for (int p = tid; p < w; p += NT) y[p] = b1[p];
+  }
+  // ---- Schur complement straight to HBM: C = gather(children) - L * U'   (2x2-block register tiles)
+  if (h > 0) {
+    double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
+    const int th = (h + 1) >> 1;
+    for (int tile = tid; tile < th * th; tile += NT) {
+      const int a0 = (tile / th) * 2, b0 = (tile % th) * 2;
+      const bool va = a0 + 1 < h, vb = b0 + 1 < h;
+      double2 acc[2][2][2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) { acc[x][y][0] = make_double2(0.0, 0.0); acc[x][y][1] = make_double2(0.0, 0.0); }
+      const int a1i = va ? a0 + 1 : a0, b1i = vb ? b0 + 1 : b0;
+      for (int p = 0; p < w; ++p) {
+        const double2 la0 = L0[a0 * w + p], la1 = L1[a0 * w + p];
+        const double2 lb0 = L0[a1i * w + p], lb1 = L1[a1i * w + p];
+        const double2 ua0 = T0[p * nf + w + b0], ua1 = T1[p * nf + w + b0];
+        const double2 ub0 = T0[p * nf + w + b1i], ub1 = T1[p * nf + w + b1i];
+        bmsub(acc[0][0][0], acc[0][0][1], la0, la1, ua0, ua1);
+        bmsub(acc[0][1][0], acc[0][1][1], la0, la1, ub0, ub1);
+        bmsub(acc[1][0][0], acc[1][0][1], lb0, lb1, ua0, ua1);
+        bmsub(acc[1][1][0], acc[1][1][1], lb0, lb1, ub0, ub1);
+      }
+      for (int ci = 0; ci < P.nchild; ++ci) {
+        const int c = M.child_list[P.child_ptr + ci];
+        const PanelDev Cp = M.panels[c];
+        const int hc = Cp.h;
+        const int* inv = M.inv + M.inv_ptr[P.child_ptr + ci];
+        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
+        const int ia0 = inv[a0], ia1 = va ? inv[a0 + 1] : -1;
+        const int ib0 = inv[b0], ib1 = vb ? inv[b0 + 1] : -1;
+        if (ia0 >= 0 && ib0 >= 0) { const double2* s = Cm + 2 * (ia0 * hc + ib0); acc[0][0][0] = cadd(acc[0][0][0], s[0]); acc[0][0][1] = cadd(acc[0][0][1], s[1]); }
+        if (ia0 >= 0 && ib1 >= 0) { const double2* s = Cm + 2 * (ia0 * hc + ib1); acc[0][1][0] = cadd(acc[0][1][0], s[0]); acc[0][1][1] = cadd(acc[0][1][1], s[1]); }
+        if (ia1 >= 0 && ib0 >= 0) { const double2* s = Cm + 2 * (ia1 * hc + ib0); acc[1][0][0] = cadd(acc[1][0][0], s[0]); acc[1][0][1] = cadd(acc[1][0][1], s[1]); }
+        if (ia1 >= 0 && ib1 >= 0) { const double2* s = Cm + 2 * (ia1 * hc + ib1); acc[1][1][0] = cadd(acc[1][1][0], s[0]); acc[1][1][1] = cadd(acc[1][1][1], s[1]); }
+      }
+      Co[2 * (a0 * h + b0)] = acc[0][0][0]; Co[2 * (a0 * h + b0) + 1] = acc[0][0][1];
+      if (vb) { Co[2 * (a0 * h + b0 + 1)] = acc[0][1][0]; Co[2 * (a0 * h + b0 + 1) + 1] = acc[0][1][1]; }
+      if (va) {
+        Co[2 * ((a0 + 1) * h + b0)] = acc[1][0][0]; Co[2 * ((a0 + 1) * h + b0) + 1] = acc[1][0][1];
+        if (vb) { Co[2 * ((a0 + 1) * h + b0 + 1)] = acc[1][1][0]; Co[2 * ((a0 + 1) * h + b0 + 1) + 1] = acc[1][1][1]; }
+      }
+    }
+    // update vector: cv[a] = gather(children) - L[a][:] y'
+    double2* cvo = Co + 2 * (size_t)h * h;
+    for (int a = tid; a < h; a += NT) {
+      double2 v = make_double2(0.0, 0.0);
+      for (int p = 0; p < w; ++p) {
+        const double2 l0 = L0[a * w + p], l1 = L1[a * w + p], y = b1[p];
+        v.x -= l0.x * y.x + l0.y * y.y;
+        v.y -= l1.x * y.x + l1.y * y.y;
+      }
+      for (int ci = 0; ci < P.nchild; ++ci) {
+        const int c = M.child_list[P.child_ptr + ci];
+        const PanelDev Cp = M.panels[c];
+        const int ia = M.inv[M.inv_ptr[P.child_ptr + ci] + a];
+        if (ia >= 0) {
+          const double2* cvc = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4) + 2 * (size_t)Cp.h * Cp.h;
+          v = cadd(v, cvc[ia]);
+        }
+      }
+      cvo[a] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: back substitution of one front: x_P = y' - U'_PP x_P(upper) - U'_PR x_R.  w <= 32.
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+  extern __shared__ double2 sm2[];
+  const int panel = panel_ids[blockIdx.x];
+  if ((int)blockIdx.y >= L.counts[2]) return;
+  const int slot = L.step[blockIdx.y];
+  const PanelDev P = M.panels[panel];
+  const int w = P.w, h = P.h, nf = w + h;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2* xs = sm2;        // [h]
+  double2* t = xs + h;      // [w]
+  double2* xv = A.xv + (size_t)slot * M.m;
+  const double2* U = reinterpret_cast<const double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
+  const double2* y = A.yv + (size_t)slot * M.m + P.first;
+  const int* sn = M.struct_nodes + P.struct_ptr;
+  for (int b = tid; b < h; b += NT) xs[b] = xv[sn[b]];
+  __syncthreads();
+  for (int p = warp; p < w; p += NT / 32) {
+    double ax = 0.0, ay = 0.0;
+    for (int b = lane; b < h; b += 32) {
+      const double2 u0 = U[2 * (p * nf + w + b)], u1 = U[2 * (p * nf + w + b) + 1], x = xs[b];
+      ax += u0.x * x.x + u0.y * x.y;
+      ay += u1.x * x.x + u1.y * x.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax += __shfl_xor_sync(0xffffffffu, ax, o);
+      ay += __shfl_xor_sync(0xffffffffu, ay, o);
+    }
+    if (lane == 0) t[p] = make_double2(y[p].x - ax, y[p].y - ay);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double2 xc = make_double2(0.0, 0.0);
+    for (int p = w - 1; p >= 0; --p) {
+      double ax = 0.0, ay = 0.0;
+      if (lane > p && lane < w) {
+        const double2 u0 = U[2 * (p * nf + lane)], u1 = U[2 * (p * nf + lane) + 1];
+        ax = u0.x * xc.x + u0.y * xc.y;
+        ay = u1.x * xc.x + u1.y * xc.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+      }
+      if (lane == p) xc = make_double2(t[p].x - ax, t[p].y - ay);
+    }
+    if (lane < w) xv[P.first + lane] = xc;
+  }
+}
+
+// V += damp * dx (slack untouched).  grid (ceil(m/8), ceil(nStep/32)), block (32, 8)
+__global__ void __launch_bounds__(256) k_update(DevModel M, Slots A, Lists L) {
+  const int ns = L.counts[2];
+  const int li = blockIdx.y * 32 + threadIdx.x;
+  const int node = blockIdx.x * 8 + threadIdx.y;
+  if (li >= ns || node >= M.m) return;
+  const int slot = L.step[li];
+  if (A.singular[slot]) return;                      // the reference breaks before applying the step
+  const int bus = M.bus_of_node[node];
+  const double2 dx = A.xv[(size_t)slot * M.m + M.elim_of_node[node]];
+  const size_t k = (size_t)bus * M.W + slot;
+  double2 v = A.V[k];
+  v.x += M.damp * dx.x;
+  v.y += M.damp * dx.y;
+  A.V[k] = v;
+}
+
+__global__ void k_poststep(DevModel M, Slots A, Lists L) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= L.counts[2]) return;
+  const int slot = L.step[li];
+  if (A.singular[slot]) { A.state[slot] = ST_DRAIN; A.numerical[slot] = 0; A.reason[slot] = 3; }
+  else if (A.iter[slot] >= M.max_iter) { A.state[slot] = ST_DRAIN; A.numerical[slot] = 0; A.reason[slot] = 1; }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalisation of finished scenarios
+// ------------------------------------------------------------------------------------------
+__global__ void k_fin_init(DevModel M, Slots A, Lists L) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= L.counts[3]) return;
+  const int slot = L.fin[li];
+  A.pvres_bits[slot] = 0ull;
+  A.vmin_bits[slot] = 0x7ff0000000000000ull;   // +Inf
+  A.vmax_bits[slot] = 0ull;
+  A.load_bits[slot] = 0ull;
+  A.viol[slot] = 0;
+  A.maxsw[slot] = 0;
+  A.rated[slot] = 0;
+}
+
+// grid (ceil(n/8), ceil(nFin/32)), block (32, 8)
+__global__ void __launch_bounds__(256) k_fin_bus(DevModel M, Slots A, Lists L, Batch Bt) {
+  const int nf = L.counts[3];
+  const int li = blockIdx.y * 32 + threadIdx.x;
+  const int bus = blockIdx.x * 8 + threadIdx.y;
+  if (li >= nf || bus >= M.n) return;
+  const int slot = L.fin[li];
+  const int scen = A.scen[slot];
+  const size_t k = (size_t)bus * M.W + slot;
+  const double2 V = A.V[k];
+  const int type = A.type[k];
+  const bool iso = A.iso[k] != 0;
+  if (Bt.r_V) Bt.r_V[(size_t)scen * M.n + bus] = V;
+  if (Bt.r_types) Bt.r_types[(size_t)scen * M.n + bus] = (unsigned char)(iso ? T_ISO : type);
+  if (!A.numerical[slot]) return;
+  const double vm = sqrt(V.x * V.x + V.y * V.y);
+  if (!iso && isfinite(vm)) {
+    atomicMin(&A.vmin_bits[slot], (unsigned long long)__double_as_longlong(vm));
+    atomicMax(&A.vmax_bits[slot], (unsigned long long)__double_as_longlong(vm));
+  }
+  if (bus == M.slack) return;
+  if (type == T_PV) {
+    if (!A.evact[k]) atomicMax(&A.pvres_bits[slot], abs_bits(vm - M.vset[bus]));   // rectangular_core_equations.jl:150-161
+    const double qmin = M.qmin[bus], qmax = M.qmax[bus];
+    if (M.qlim_enabled && isfinite(qmin) && isfinite(qmax)) {                       // rectangular_network_solver.jl:64-95
+      const double2 Sc = cmul(V, cconj(A.I[k]));
+      const double qc = Sc.y + (A.qload_s ? A.qload_s[k] : M.qload[bus]);
+      if (qc < qmin - M.tol || qc > qmax + M.tol) atomicAdd(&A.viol[slot], 1);
+    }
+  }
+  if (A.evcnt[k] >= max(M.guard, 1)) atomicOr(&A.maxsw[slot], 1);                  // :1027-1036
+}
+
+// branch flows and loading (losses.jl:53-85, contingency.jl:165-176). grid (ceil(nbr/8), ceil(nFin/32))
+__global__ void __launch_bounds__(256) k_fin_branch(DevModel M, Slots A, Lists L) {
+  const int nf = L.counts[3];
+  const int li = blockIdx.y * 32 + threadIdx.x;
+  const int br = blockIdx.x * 8 + threadIdx.y;
+  if (li >= nf || br >= M.nbr) return;
+  const int slot = L.fin[li];
+  if (!A.numerical[slot] || !M.br_status[br]) return;
+  const double rt = M.rating[br];
+  if (!(isfinite(rt) && rt > 0.0)) return;
+  const int no = A.out_cnt[slot];
+  for (int o = 0; o < no; ++o)
+    if (A.out_br[slot * MAXOUT + o] == br) return;
+  const int f = M.br_from[br], t = M.br_to[br];
+  const double2 Vf = A.V[(size_t)f * M.W + slot], Vt = A.V[(size_t)t * M.W + slot];
+  const double2 If = cadd(cmul(M.y11[br], Vf), cmul(M.y12[br], Vt));
+  const double2 It = cadd(cmul(M.y22[br], Vt), cmul(M.y21[br], Vf));
+  const double2 Sf = cmul(Vf, cconj(If)), St = cmul(Vt, cconj(It));
+  const double sf = hypot(Sf.x, Sf.y), st = hypot(St.x, St.y);
+  const double loading = 100.0 * fmax(sf, st) * M.base_mva / rt;
+  atomicMax(&A.load_bits[slot], abs_bits(loading));
+  A.rated[slot] = 1;
+}
+
+__global__ void k_fin_write(DevModel M, Slots A, Lists L, Batch Bt) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= L.counts[3]) return;
+  const int slot = L.fin[li];
+  const int scen = A.scen[slot];
+  int conv = A.numerical[slot];
+  int reason = A.reason[slot];
+  if (conv) {
+    const double pvres = bits_double(A.pvres_bits[slot]);
+    if (pvres > M.tol) { conv = 0; reason = 5; }
+    if (M.qlim_enabled && A.viol[slot] > 0) { conv = 0; reason = 4; }
+    if (M.freeze && A.maxsw[slot]) { conv = 0; reason = 6; }
+  }
+  Bt.r_conv[scen] = conv;
+  Bt.r_status[scen] = reason;
+  Bt.r_iter[scen] = A.iter[slot];
+  Bt.r_nsw[scen] = A.nev[slot];
+  Bt.r_fm[scen] = A.fm[slot];
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  if (conv) {
+    const double vmin = bits_double(A.vmin_bits[slot]), vmax = bits_double(A.vmax_bits[slot]);
+    Bt.r_vmin[scen] = isfinite(vmin) ? vmin : nan;
+    Bt.r_vmax[scen] = (vmax > 0.0) ? vmax : nan;
+    Bt.r_load[scen] = A.rated[slot] ? bits_double(A.load_bits[slot]) : nan;
+  } else {
+    Bt.r_vmin[scen] = nan; Bt.r_vmax[scen] = nan; Bt.r_load[scen] = nan;
+  }
+  A.state[slot] = ST_IDLE;
+  A.scen[slot] = -1;
+}
+
+// pack summary records {i32 conv,status,iter,nsw; f64 fm,vmin,vmax,load} for the NCCL gather
+__global__ void k_pack_summary(Batch Bt, unsigned char* out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= Bt.B) return;
+  int* ip = reinterpret_cast<int*>(out + (size_t)s * 48);
+  double* dp = reinterpret_cast<double*>(out + (size_t)s * 48 + 16);
+  ip[0] = Bt.r_conv[s]; ip[1] = Bt.r_status[s]; ip[2] = Bt.r_iter[s]; ip[3] = Bt.r_nsw[s];
+  dp[0] = Bt.r_fm[s]; dp[1] = Bt.r_vmin[s]; dp[2] = Bt.r_vmax[s]; dp[3] = Bt.r_load[s];
+}
+
+}  // namespace sblx

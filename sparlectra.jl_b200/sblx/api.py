@@ -1,0 +1,450 @@
+"""Host-side mirror of the reference's plugin / contingency interface, driving the
+CUDA engine through the C ABI (include/sblx.h).
+
+Names, argument meaning and error behaviour follow the reference
+(`src/solver_interface.jl`, `src/contingency.jl`): `PFModel`, `PFSolution`,
+`AbstractExternalSolver`/`solvePf`, `buildPfModel`, `mismatchInf`,
+`runpf_external`, `ContingencyCase`, `ContingencyResult`, `generateN1Branches`,
+`runContingenciesBatched` (= `runContingencies!` with the batched backend).
+Failures of a scenario are REPORTED in the result, never thrown
+(src/contingency.jl:72-73); argument errors do throw (src/contingency.jl:270).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+import numpy as np
+import scipy.sparse as sp
+
+from . import lib as L
+from . import model as M
+
+STATUS_TEXT = {
+    0: None,
+    1: "power flow did not converge (status 1)",
+    2: "power flow did not converge (status 1)",
+    3: "power flow did not converge (status 1)",
+    4: "power flow did not converge (status 1)",
+    5: "power flow did not converge (status 1)",
+    6: "power flow did not converge (status 1)",
+    7: "islanded without reference",
+    8: "unknown branch",
+    9: "islanded (island-wise solve not supported by the batched backend)",
+}
+REASON = {0: "none", 1: "nr_mismatch_not_converged", 2: "nr_nonfinite", 3: "singular_newton_step",
+          4: "remaining_pv_q_limit_violations", 5: "active_pv_voltage_residual", 6: "max_switching_exceeded",
+          7: "islanded_without_reference", 8: "unknown_branch", 9: "islanded_unsupported"}
+
+
+# ---------------------------------------------------------------------------
+# PFModel / PFSolution (src/solver_interface.jl:51-82)
+# ---------------------------------------------------------------------------
+@dataclass
+class PFModel:
+    Ybus: sp.csc_matrix
+    baseMVA: float
+    busIdx_net: np.ndarray
+    busType: np.ndarray          # uint8 codes (model.BUS_*)
+    slack_idx: int               # 0-based here
+    Vset: np.ndarray
+    Sspec: np.ndarray
+    V0: np.ndarray
+    qmin_pu: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    qmax_pu: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    arrays: Optional[M.ModelArrays] = None
+
+
+@dataclass
+class PFSolution:
+    V: np.ndarray
+    converged: bool
+    iters: int
+    residual_inf: float
+    meta: object = None
+
+
+class AbstractExternalSolver:
+    pass
+
+
+def buildPfModel(grid, flatstart=None, include_limits=True) -> PFModel:
+    """buildPfModel (src/solver_interface.jl:193-295) on grid tables."""
+    a = M.build_arrays(grid, flatstart=flatstart)
+    return PFModel(Ybus=a.Y, baseMVA=a.baseMVA, busIdx_net=np.arange(a.n), busType=a.bus_type, slack_idx=a.slack,
+                   Vset=a.vset, Sspec=a.s_spec, V0=a.v0,
+                   qmin_pu=a.qmin if include_limits else np.zeros(0), qmax_pu=a.qmax if include_limits else np.zeros(0),
+                   arrays=a)
+
+
+def mismatchInf(model: PFModel, V) -> float:
+    """mismatchInf (src/solver_interface.jl:310-313): inf-norm of the rectangular PQ/PV residual."""
+    Sc = V * np.conj(model.Ybus @ V)
+    ns = np.arange(len(V)) != model.slack_idx
+    dp = np.abs(Sc.real - model.Sspec.real)[ns]
+    second = np.where(model.busType == M.BUS_PV, np.abs(np.abs(V) - model.Vset), np.abs(Sc.imag - model.Sspec.imag))[ns]
+    return float(max(dp.max(initial=0.0), second.max(initial=0.0)))
+
+
+# ---------------------------------------------------------------------------
+# Engine: one handle = one grid on one GPU
+# ---------------------------------------------------------------------------
+class Engine:
+    def __init__(self, arrays: M.ModelArrays, **options):
+        self.lib = L.load()
+        self.a = arrays
+        self.n = arrays.n
+        self.opt = L.default_options(index_base=0, base_mva=arrays.baseMVA, **options)
+        Y = arrays.Y.tocsc()
+        Y.sort_indices()
+        self._keep = dict(
+            colptr=np.ascontiguousarray(Y.indptr, np.int64), rowval=np.ascontiguousarray(Y.indices, np.int64),
+            nz=L.c128_to_f64(Y.data), bt=np.ascontiguousarray(arrays.bus_type, np.uint8),
+            vset=np.ascontiguousarray(arrays.vset, float), s=L.c128_to_f64(arrays.s_spec), v0=L.c128_to_f64(arrays.v0),
+            qmin=np.ascontiguousarray(arrays.qmin, float), qmax=np.ascontiguousarray(arrays.qmax, float),
+            ql=np.ascontiguousarray(arrays.qload, float), bf=np.ascontiguousarray(arrays.br_from, np.int32),
+            bt2=np.ascontiguousarray(arrays.br_to, np.int32), y11=L.c128_to_f64(arrays.y11), y12=L.c128_to_f64(arrays.y12),
+            y21=L.c128_to_f64(arrays.y21), y22=L.c128_to_f64(arrays.y22),
+            rt=np.ascontiguousarray(arrays.br_rating, float), st=np.ascontiguousarray(arrays.br_status, np.uint8))
+        k = self._keep
+        h = C.c_void_p()
+        rc = self.lib.sblx_create(C.byref(h), self.n, L.ptr(k["colptr"], L.c_i64p), L.ptr(k["rowval"], L.c_i64p),
+                                  L.ptr(k["nz"], L.c_f64p), arrays.slack, L.ptr(k["bt"], L.c_u8p), L.ptr(k["vset"], L.c_f64p),
+                                  L.ptr(k["s"], L.c_f64p), L.ptr(k["v0"], L.c_f64p), L.ptr(k["qmin"], L.c_f64p),
+                                  L.ptr(k["qmax"], L.c_f64p), L.ptr(k["ql"], L.c_f64p), len(arrays.br_from),
+                                  L.ptr(k["bf"], L.c_i32p), L.ptr(k["bt2"], L.c_i32p), L.ptr(k["y11"], L.c_f64p),
+                                  L.ptr(k["y12"], L.c_f64p), L.ptr(k["y21"], L.c_f64p), L.ptr(k["y22"], L.c_f64p),
+                                  L.ptr(k["rt"], L.c_f64p), L.ptr(k["st"], L.c_u8p), C.byref(self.opt))
+        L.check(rc, None)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sblx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- info -------------------------------------------------------------
+    def info(self) -> dict:
+        i = L.Info()
+        L.check(self.lib.sblx_get_info(self.h, C.byref(i)), self.h)
+        return L.as_dict(i)
+
+    def stats(self) -> dict:
+        s = L.Stats()
+        L.check(self.lib.sblx_get_stats(self.h, C.byref(s)), self.h)
+        return L.as_dict(s)
+
+    def set_v0(self, v0):
+        v = L.c128_to_f64(v0)
+        L.check(self.lib.sblx_set_v0(self.h, L.ptr(v, L.c_f64p)), self.h)
+
+    def set_locked_pv(self, buses):
+        b = np.ascontiguousarray(buses, np.int32)
+        L.check(self.lib.sblx_set_locked_pv(self.h, len(b), L.ptr(b, L.c_i32p)), self.h)
+
+    # -- solves -------------------------------------------------------------
+    @staticmethod
+    def _alloc(B, n, want_v, want_types):
+        r = dict(converged=np.zeros(B, np.uint8), status=np.zeros(B, np.int32), iterations=np.zeros(B, np.int32),
+                 n_switch_events=np.zeros(B, np.int32), island_count=np.zeros(B, np.int32),
+                 final_mismatch=np.zeros(B), vmin_pu=np.zeros(B), vmax_pu=np.zeros(B), max_loading_pct=np.zeros(B))
+        if want_v:
+            r["V"] = np.zeros((B, n), np.complex128)
+        if want_types:
+            r["bus_type_final"] = np.zeros((B, n), np.uint8)
+        return r
+
+    @staticmethod
+    def _results_struct(r):
+        s = L.Results()
+        s.converged = L.ptr(r["converged"], L.c_u8p)
+        s.status = L.ptr(r["status"], L.c_i32p)
+        s.iterations = L.ptr(r["iterations"], L.c_i32p)
+        s.n_switch_events = L.ptr(r["n_switch_events"], L.c_i32p)
+        s.island_count = L.ptr(r["island_count"], L.c_i32p)
+        s.final_mismatch = L.ptr(r["final_mismatch"], L.c_f64p)
+        s.vmin_pu = L.ptr(r["vmin_pu"], L.c_f64p)
+        s.vmax_pu = L.ptr(r["vmax_pu"], L.c_f64p)
+        s.max_loading_pct = L.ptr(r["max_loading_pct"], L.c_f64p)
+        s.V = L.ptr(r["V"].view(np.float64), L.c_f64p) if "V" in r else None
+        s.bus_type_final = L.ptr(r["bus_type_final"], L.c_u8p) if "bus_type_final" in r else None
+        return s
+
+    @staticmethod
+    def pack_outages(cases):
+        """list of branch-id lists -> (ptr int32[B+1], br int32[])"""
+        ptr = np.zeros(len(cases) + 1, np.int32)
+        for i, c in enumerate(cases):
+            ptr[i + 1] = ptr[i] + len(c)
+        br = np.array([b for c in cases for b in c], np.int32) if ptr[-1] > 0 else np.zeros(1, np.int32)
+        return ptr, br
+
+    def solve_outages(self, cases, want_v=True, want_types=True) -> dict:
+        B = len(cases)
+        optr, obr = self.pack_outages(cases) if not isinstance(cases, tuple) else cases
+        B = len(optr) - 1
+        r = self._alloc(B, self.n, want_v, want_types)
+        s = self._results_struct(r)
+        L.check(self.lib.sblx_solve_outages(self.h, B, L.ptr(optr, L.c_i32p), L.ptr(obr, L.c_i32p), C.byref(s)), self.h)
+        return r
+
+    def stage_outages(self, optr, obr, want_v=False, want_types=False):
+        L.check(self.lib.sblx_stage_outages(self.h, len(optr) - 1, L.ptr(optr, L.c_i32p), L.ptr(obr, L.c_i32p),
+                                            int(want_v), int(want_types)), self.h)
+        self._staged = (len(optr) - 1, want_v, want_types)
+
+    def run_staged(self):
+        L.check(self.lib.sblx_run_staged(self.h), self.h)
+
+    def fetch(self) -> dict:
+        B, wv, wt = self._staged
+        r = self._alloc(B, self.n, wv, wt)
+        s = self._results_struct(r)
+        L.check(self.lib.sblx_fetch_results(self.h, C.byref(s)), self.h)
+        return r
+
+    def device_summary(self):
+        p = C.c_void_p()
+        nb = C.c_int64()
+        L.check(self.lib.sblx_device_summary(self.h, C.byref(p), C.byref(nb)), self.h)
+        return p.value, nb.value
+
+    def solve_injections(self, S, qload=None, want_v=True, want_types=True) -> dict:
+        S = np.ascontiguousarray(S, np.complex128)
+        B = S.shape[0]
+        r = self._alloc(B, self.n, want_v, want_types)
+        s = self._results_struct(r)
+        ql = None if qload is None else np.ascontiguousarray(qload, float)
+        L.check(self.lib.sblx_solve_injections(self.h, B, L.ptr(S.view(np.float64), L.c_f64p), L.ptr(ql, L.c_f64p), C.byref(s)), self.h)
+        return r
+
+    def solve_one(self, v_start=None):
+        vout = np.zeros(self.n, np.complex128)
+        c = C.c_uint8()
+        it = C.c_int32()
+        res = C.c_double()
+        st = C.c_int32()
+        vs = None if v_start is None else L.c128_to_f64(v_start)
+        L.check(self.lib.sblx_solve_one(self.h, L.ptr(vs, L.c_f64p), L.ptr(vout.view(np.float64), L.c_f64p), C.byref(c),
+                                        C.byref(it), C.byref(res), C.byref(st)), self.h)
+        return vout, bool(c.value), int(it.value), float(res.value), int(st.value)
+
+    # -- parity hooks -------------------------------------------------------
+    def pattern(self):
+        i = self.info()
+        rp = np.zeros(i["m"] + 1, np.int64)
+        col = np.zeros(i["nnz_j_blocks"], np.int32)
+        L.check(self.lib.sblx_debug_pattern(self.h, L.ptr(rp, L.c_i64p), L.ptr(col, L.c_i32p)), self.h)
+        return rp, col
+
+    def newton_step(self, V, outages=(), bus_type=None):
+        i = self.info()
+        m, nb = i["m"], i["nnz_j_blocks"]
+        F = np.zeros(2 * m)
+        J = np.zeros(4 * nb)
+        dx = np.zeros(2 * m)
+        mm = np.zeros(1)
+        ob = np.ascontiguousarray(list(outages) or [0], np.int32)
+        bt = None if bus_type is None else np.ascontiguousarray(bus_type, np.uint8)
+        v = L.c128_to_f64(V)
+        L.check(self.lib.sblx_debug_newton_step(self.h, len(outages), L.ptr(ob, L.c_i32p), L.ptr(bt, L.c_u8p),
+                                                L.ptr(v, L.c_f64p), L.ptr(F, L.c_f64p), L.ptr(J, L.c_f64p),
+                                                L.ptr(dx, L.c_f64p), L.ptr(mm, L.c_f64p)), self.h)
+        return F, J.reshape(nb, 2, 2), dx, float(mm[0])
+
+    def host_selftest(self, seed=1) -> float:
+        r = C.c_double()
+        L.check(self.lib.sblx_debug_host_selftest(self.h, seed, C.byref(r)), self.h)
+        return r.value
+
+
+def analyze_only(Y: sp.csc_matrix, slack: int, **options):
+    """Symbolic analysis without CUDA (CPU tests)."""
+    lib = L.load()
+    Y = sp.csc_matrix(Y)
+    Y.sort_indices()
+    opt = L.default_options(index_base=0, **options)
+    cp = np.ascontiguousarray(Y.indptr, np.int64)
+    rv = np.ascontiguousarray(Y.indices, np.int64)
+    info = L.Info()
+    res = C.c_double()
+    L.check(lib.sblx_analyze_only(Y.shape[0], L.ptr(cp, L.c_i64p), L.ptr(rv, L.c_i64p), slack, C.byref(opt), C.byref(info),
+                                  C.byref(res)), None)
+    return L.as_dict(info), res.value
+
+
+# ---------------------------------------------------------------------------
+# B200BatchSolver: AbstractExternalSolver backend (src/solver_interface.jl:134-145;
+# template: ext/SparlectraAnalyticLoadFlowExt.jl:44-136)
+# ---------------------------------------------------------------------------
+class B200BatchSolver(AbstractExternalSolver):
+    def __init__(self, **options):
+        self.options = options
+
+
+def solvePf(solver: AbstractExternalSolver, model: PFModel, tol: float = 1e-8, **kwargs) -> PFSolution:
+    """solvePf(solver, model; tol, kwargs...) -> PFSolution (src/solver_interface.jl:143-145)."""
+    if not isinstance(solver, B200BatchSolver):
+        raise NotImplementedError("solvePf(::AbstractExternalSolver, ::PFModel) is not implemented for this solver.")
+    a = model.arrays
+    if a is None:
+        raise ValueError("solvePf: model was not built by buildPfModel")
+    opts = dict(solver.options)
+    opts.update(kwargs)
+    eng = Engine(a, tol=tol, **opts)
+    try:
+        V, conv, it, res, st = eng.solve_one(model.V0)
+    finally:
+        eng.close()
+    return PFSolution(V=V, converged=conv, iters=it, residual_inf=res, meta=dict(status=st, reason=REASON.get(st)))
+
+
+def runpf_external(grid, solver, tol=1e-8, flatstart=None, include_limits=False, **solver_kwargs):
+    """runpf_external! (src/solver_interface.jl:402-442): build model, solve, re-check the
+    canonical mismatch, return (iters, status, sol)."""
+    model = buildPfModel(grid, flatstart=flatstart, include_limits=include_limits)
+    sol = solvePf(solver, model, tol=tol, qlimits_enabled=int(include_limits), **solver_kwargs)
+    res = mismatchInf(model, sol.V) if (sol.residual_inf <= 0.0 or not math.isfinite(sol.residual_inf)) else sol.residual_inf
+    sol2 = PFSolution(V=sol.V, converged=sol.converged and res <= tol, iters=sol.iters, residual_inf=res, meta=sol.meta)
+    return sol2.iters, (0 if sol2.converged else 1), sol2
+
+
+# ---------------------------------------------------------------------------
+# contingency API (src/contingency.jl)
+# ---------------------------------------------------------------------------
+@dataclass
+class ContingencyCase:
+    name: str
+    kind: str = "branch"
+    element: str = ""
+
+    def __post_init__(self):
+        if self.kind != "branch":
+            raise ValueError(f"ContingencyCase: only kind = :branch is supported in this version, got :{self.kind}.")
+        if not self.element:
+            self.element = self.name
+
+
+@dataclass
+class ContingencyResult:
+    name: str
+    converged: bool
+    iterations: int
+    max_vm_pu: float
+    min_vm_pu: float
+    max_branch_loading_pct: float
+    overloaded_branches: list
+    voltage_violations: list
+    island_count: int
+    error: Optional[str]
+
+
+def generateN1Branches(grid, include_transformers: bool = True):
+    """generateN1Branches (src/contingency.jl:99-119): one case per in-service branch;
+    parallel circuits sharing a name are disambiguated as "<name>#<branchIdx>" (1-based)."""
+    count = {}
+    for nm in grid.br_name:
+        count[nm] = count.get(nm, 0) + 1
+    cases = []
+    for k in range(grid.nbranch):
+        if grid.br_status[k] != 1:
+            continue
+        if not include_transformers and grid.br_ratio[k] != 0.0:
+            continue
+        nm = grid.br_name[k]
+        el = f"{nm}#{k + 1}" if count[nm] > 1 else nm
+        cases.append(ContingencyCase(el, "branch", el))
+    return cases
+
+
+def _resolve_branch(grid, element: str):
+    """_resolve_contingency_branch (src/contingency.jl:124-135)."""
+    pos = element.rfind("#")
+    if pos >= 0:
+        try:
+            idx = int(element[pos + 1:])
+        except ValueError:
+            return None
+        name = element[:pos]
+        if 1 <= idx <= grid.nbranch and grid.br_name[idx - 1] == name:
+            return idx - 1
+        return None
+    for k, nm in enumerate(grid.br_name):
+        if nm == element:
+            return k
+    return None
+
+
+def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30, tol=1e-8, backend=None,
+                            return_raw=False, **kwargs):
+    """runContingencies! (src/contingency.jl:257-319) with the batched B200 backend: the
+    base case is solved first (warm-start template; on failure the cases start flat), then
+    ALL cases go to the GPU in one call.  Results come back in input order."""
+    if not (vm_min_pu < vm_max_pu):
+        raise ValueError("runContingencies!: vm_min_pu must be below vm_max_pu.")
+    if len(cases) == 0:
+        return []
+    opts = dict(backend.options) if isinstance(backend, B200BatchSolver) else {}
+    opts.update(kwargs)
+    opts.update(max_iter=maxIte, tol=tol, vm_min_pu=vm_min_pu, vm_max_pu=vm_max_pu,
+                cooldown_iters=grid.cooldown_iters, q_hyst_pu=grid.q_hyst_pu)
+    a = M.build_arrays(grid)
+    eng = Engine(a, **opts)
+    try:
+        Vb, conv, _, _, _ = eng.solve_one(None)
+        if conv:
+            # template nodes carry the solved vm / va (rectangular_result_updates.jl:30-47)
+            vm, va = np.abs(Vb), np.degrees(np.angle(Vb))
+            a2 = M.build_arrays(grid, vm=vm, va_deg=va, flatstart=False)
+        else:
+            a2 = M.build_arrays(grid, flatstart=True)           # contingency.jl:283-287
+            eng.close()
+            eng = Engine(a2, **opts)                              # Vset may differ for a flat start
+        eng.set_v0(a2.v0)
+        idx = [_resolve_branch(grid, c.element) for c in cases]
+        lists = [[k] if k is not None else [-1] for k in idx]
+        raw = eng.solve_outages(lists, want_v=True, want_types=return_raw)
+    finally:
+        eng.close()
+    out = []
+    for i, c in enumerate(cases):
+        st = int(raw["status"][i])
+        if idx[i] is None:
+            out.append(ContingencyResult(c.name, False, 0, math.nan, math.nan, math.nan, [], [], 0,
+                                         f"unknown branch {c.element} (not found in net.branchVec)"))
+            continue
+        if not raw["converged"][i]:
+            out.append(ContingencyResult(c.name, False, int(raw["iterations"][i]), math.nan, math.nan, math.nan, [], [],
+                                         int(raw["island_count"][i]), STATUS_TEXT.get(st, f"status {st}")))
+            continue
+        V = raw["V"][i]
+        vmag = np.abs(V)
+        deg = np.bincount(np.concatenate([grid.br_from, grid.br_to]),
+                          weights=np.concatenate([grid.br_status == 1, grid.br_status == 1]).astype(float), minlength=grid.n)
+        k = idx[i]
+        deg[grid.br_from[k]] -= 1
+        deg[grid.br_to[k]] -= 1
+        live = deg > 0
+        viol = [grid.bus_name[b] for b in np.flatnonzero(live & ((vmag < vm_min_pu) | (vmag > vm_max_pu)))]
+        over = []
+        if np.isfinite(raw["max_loading_pct"][i]) and raw["max_loading_pct"][i] > 100.0:
+            y11, y12, y21, y22 = a.y11, a.y12, a.y21, a.y22
+            f, t = grid.br_from, grid.br_to
+            sf = np.abs(V[f] * np.conj(y11 * V[f] + y12 * V[t]))
+            stt = np.abs(V[t] * np.conj(y22 * V[t] + y21 * V[f]))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                loading = 100.0 * np.maximum(sf, stt) * grid.baseMVA / grid.br_rating
+            ok = (grid.br_status == 1) & np.isfinite(grid.br_rating) & (grid.br_rating > 0)
+            ok[k] = False
+            over = [grid.br_name[b] for b in np.flatnonzero(ok & (loading > 100.0))]
+        out.append(ContingencyResult(c.name, True, int(raw["iterations"][i]), float(raw["vmax_pu"][i]),
+                                     float(raw["vmin_pu"][i]), float(raw["max_loading_pct"][i]), over, viol,
+                                     int(raw["island_count"][i]), None))
+    return (out, raw) if return_raw else out
