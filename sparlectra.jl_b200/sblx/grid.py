@@ -314,7 +314,7 @@ def tiled_grid(max_buses: int = None, rows: int = None, cols: int = None, *, r=0
                base_mva=100.0, load_mw_per_right_corner=50.0, load_mvar_per_right_corner=15.0,
                generation_balance=0.995, vm_slack=1.0, vm_flat=1.0,
                augment: bool = False, seed: int = 20260724, pv_every: int = 7, pv_vm: float = 1.02,
-               pv_q_mvar: float = 12.0, load_mw=(0.5, 2.0), load_q_ratio=0.3, rating_mva: float = NAN) -> Grid:
+               pv_q_mvar: float = 30.0, load_mw=(0.5, 2.0), load_q_ratio=0.3, rating_mva: float = NAN) -> Grid:
     """build_synthetic_tiled_grid_net (src/synthetic_grids.jl:88-171): rows x cols
     buses named B_rrr_ccc, horizontal, vertical and one upper-left -> lower-right
     diagonal branch per tile (in that emit order), slack at (1,1), a
