@@ -838,8 +838,9 @@ def run_contingencies(grid, cases, vm_min=0.9, vm_max=1.1, maxiter=30, tol=1e-8,
     vm, va, flat, _ = solve_base(grid, maxiter, tol, **kw)
     out = []
     for ci, removed in enumerate(cases):
-        name = "+".join(grid.br_name[k] for k in removed) if len(removed) else "base"
-        if any((k < 0 or k >= grid.nbranch) for k in removed):
+        bad = any((k < 0 or k >= grid.nbranch) for k in removed)
+        name = "base" if not len(removed) else ("?" if bad else "+".join(grid.br_name[k] for k in removed))
+        if bad:
             out.append(ContingencyResult(name, False, 0, math.nan, math.nan, math.nan, [], [], 0,
                                          "unknown branch", reason=R_UNKNOWN_BRANCH))
             continue

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <random>
@@ -15,6 +16,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <cuda_profiler_api.h>
 
 #include "kernels.cuh"
 #include "symbolic.h"
@@ -836,7 +839,11 @@ static void run_staged(sblx_handle* h) {
   const int64_t nq = h->nq;
   double t_mis = 0, t_jac = 0, t_fac = 0, t_sol = 0, t_oth = 0;
   bool have_prev = false;
+  // SBLX_PROFILE_TICK=k brackets tick k (1-based) of this run with cudaProfilerStart/Stop (ncu --profile-from-start off)
+  const char* ptick_env = getenv("SBLX_PROFILE_TICK");
+  const long ptick = (ptick_env && nq > 1) ? atol(ptick_env) : 0;
   while (running > 0 || qhead < nq) {
+    if (ptick > 0 && st.ticks + 1 == ptick) cudaProfilerStart();
     const int64_t assign = std::min<int64_t>(W - running, nq - qhead);
     const int nactive_ub = (int)(running + assign);   // exact: DRAIN slots are excluded on the device side
     CK(cudaEventRecord(ev[1], s));
@@ -934,6 +941,7 @@ static void run_staged(sblx_handle* h) {
       running -= nfin;
     }
     CK(cudaEventRecord(ev[7], s));
+    if (ptick > 0 && st.ticks == ptick) { cudaStreamSynchronize(s); cudaProfilerStop(); }
     have_prev = true;
     CK(cudaGetLastError());
     if (st.ticks > (int64_t)(nq + 8) * (h->opt.max_iter + 2)) throw std::runtime_error("sblx: tick loop did not terminate");

@@ -1,0 +1,169 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared
+symbol, symbolic analysis self-tests, model arrays agree with the oracle's restatement, API
+argument errors throw, and the solve entry points fail loudly without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sparlectra_oracle as O
+from sblx import api, grid as G, lib as L, model as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sblx.h")).read()
+    declared = set(re.findall(r"\b(sblx_[a-z0-9_]+)\s*\(", hdr))
+    lib = L.load()
+    assert lib.sblx_version() == 100
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(L.EXPORTS)
+
+
+def test_options_struct_abi_size():
+    o = L.default_options()
+    assert o.struct_size == __import__("ctypes").sizeof(L.Options)
+    assert (o.max_iter, o.qlimit_start_iter, o.guard_max_switches, o.index_base) == (30, 2, 10, 1)
+    assert o.tol == 1e-8 and o.damp == 1.0
+
+
+@pytest.mark.parametrize("maker", [G.case14, G.warmup_case118, lambda: G.tiled_grid(rows=9, cols=13, augment=True, pv_every=4),
+                                   lambda: G.tiled_grid(rows=40, cols=40)])
+@pytest.mark.parametrize("ordering", [0, 1, 2])
+def test_symbolic_selftest(maker, ordering):
+    g = maker()
+    a = M.build_arrays(g)
+    info, resid = api.analyze_only(a.Y, a.slack, ordering=ordering)
+    assert resid < 1e-12
+    assert info["m"] == g.n - 1 and info["nnz_j_scalar"] == 4 * info["nnz_j_blocks"]
+    assert info["nnz_lu_scalar"] >= info["nnz_j_scalar"]
+    assert info["algorithmic_bytes_per_iteration"] == 16 * info["nnz_j_scalar"] + 16 * info["nnz_lu_scalar"] + 128 * g.n
+
+
+def test_symbolic_fill_regression_values():
+    """nnz(L+U) of the block analysis on the tiled grids (SURVEY.md 8 table quotes 0.51-0.75 M scalar
+    entries for 54x54 and 2.24-3.79 M for 100x100 with scalar MMD/COLAMD; the 2x2-block ND/MD analysis
+    lands at the low end)."""
+    g = G.tiled_grid(rows=54, cols=54)
+    a = M.build_arrays(g)
+    info, resid = api.analyze_only(a.Y, a.slack)
+    assert resid < 1e-12
+    assert 0.45e6 < info["nnz_lu_scalar"] < 0.75e6
+    assert info["nnz_j_scalar"] == 4 * (19982 - (1 + 2 * 3))       # nnzY minus the slack row/col (3 neighbours)
+    assert info["n_levels"] < 40
+
+
+@pytest.mark.parametrize("maker", [G.case14, G.warmup_case118, G.warmup_case3, lambda: G.test3bus(qlim_min=-15.0, qlim_max=15.0),
+                                   lambda: G.tiled_grid(rows=7, cols=9, augment=True, pv_every=3)])
+def test_model_arrays_match_oracle_restatement(maker):
+    g = maker()
+    a = M.build_arrays(g)
+    assert abs(a.Y - O.create_ybus(g)).max() < 1e-12
+    t = O.bus_types_from_prosumers(g)
+    assert np.array_equal(a.bus_type, t.astype(np.uint8))
+    assert np.allclose(a.s_spec, O.complex_svec(g), atol=1e-15)
+    assert np.allclose(a.qload, O.qload_pu(g), atol=1e-15)
+    qmin, qmax = O.q_limits_pu(g)
+    assert np.array_equal(np.isfinite(a.qmin), np.isfinite(qmin)) and np.allclose(a.qmin[np.isfinite(qmin)], qmin[np.isfinite(qmin)])
+    assert np.array_equal(np.isfinite(a.qmax), np.isfinite(qmax)) and np.allclose(a.qmax[np.isfinite(qmax)], qmax[np.isfinite(qmax)])
+    vset = O.voltage_setpoints(g, g.vm0)
+    assert np.allclose(a.vset, vset)
+    V0, slack = O.initial_vrect(g, g.vm0, g.va0_deg, t)
+    V0[slack] = O._mag_keep_angle(V0[slack], vset[slack])
+    assert slack == a.slack and np.allclose(a.v0, V0, atol=1e-15)
+    for k in range(g.nbranch):
+        st = O.branch_stamp(g.br_r[k], g.br_x[k], g.br_b[k], g.br_g[k], g.br_ratio[k], g.br_shift_deg[k])
+        assert np.allclose([a.y11[k], a.y12[k], a.y21[k], a.y22[k]], st, rtol=1e-14, atol=1e-14)
+
+
+def test_phase_shifter_stamp_is_not_symmetric():
+    gb = G.GridBuilder("ps", 100.0)
+    gb.add_bus("A"); gb.add_bus("B")
+    gb.add_pi_line("A", "B", 0.01, 0.1, 0.0, ratio=1.0, shift_deg=30.0)
+    gb.add_prosumer("A", "EXTERNALNETWORKINJECTION", vm_pu=1.0, va_deg=0.0, reference=True)
+    g = gb.build()
+    y11, y12, y21, y22 = M.branch_stamps(g)
+    assert abs(y12[0] - y21[0]) > 1e-3 and abs(y11[0] - y22[0]) < 1e-12
+
+
+def test_tiled_grid_generator_shape():
+    """src/synthetic_grids.jl:150: rows*(cols-1) + (rows-1)*cols + (rows-1)*(cols-1) branches; dims per :26-51."""
+    assert G.choose_tiled_grid_dims(2916) == (54, 54)
+    assert G.choose_tiled_grid_dims(10000) == (100, 100)
+    assert G.choose_tiled_grid_dims(10) == (5, 2)      # largest area first, then aspect score
+    g = G.tiled_grid(10000)
+    assert g.n == 10000 and g.nbranch == 29601
+    g = G.tiled_grid(rows=54, cols=54)
+    assert g.nbranch == 8533
+    assert g.bus_name[0] == "B_001_001" and g.bus_name[-1] == "B_054_054"
+    a = M.build_arrays(g)
+    assert a.slack == 0 and (a.bus_type == M.BUS_PV).sum() == 0          # stock grid: one non-regulating generator
+    assert abs(a.s_spec[53 * 54].real - 0.995) < 1e-12 and abs(a.s_spec[53].real + 0.5) < 1e-12
+
+
+def test_contingency_api_shapes_and_errors():
+    g = G.case14()
+    cases = api.generateN1Branches(g)
+    assert len(cases) == 20 and all(c.kind == "branch" for c in cases)
+    assert len(api.generateN1Branches(g, include_transformers=False)) == 17
+    with pytest.raises(ValueError):
+        api.ContingencyCase("x", "bus", "x")
+    with pytest.raises(ValueError):
+        api.runContingenciesBatched(g, cases, vm_min_pu=1.2, vm_max_pu=1.1)
+    assert api.runContingenciesBatched(g, []) == []
+    assert api._resolve_branch(g, cases[3].element) == 3
+    assert api._resolve_branch(g, "NO_SUCH_BRANCH") is None
+    with pytest.raises(NotImplementedError):
+        api.solvePf(api.AbstractExternalSolver(), api.buildPfModel(g))
+
+
+def test_create_validates_arguments():
+    g = G.case14()
+    a = M.build_arrays(g)
+    bad = M.build_arrays(g)
+    bad.bus_type = bad.bus_type.copy()
+    bad.bus_type[3] = M.BUS_SLACK
+    with pytest.raises(L.SblxError):
+        api.Engine(bad)
+    with pytest.raises(L.SblxError):
+        api.Engine(a, max_iter=0)
+    e = api.Engine(a)
+    assert e.info()["n"] == 14 and e.host_selftest() < 1e-12
+    e.close()
+
+
+def test_mismatch_inf_matches_oracle():
+    g = G.case14()
+    model = api.buildPfModel(g)
+    r = O.runpf(g, g.vm0, g.va0_deg, ())
+    assert api.mismatchInf(model, r.V) <= 1e-8
+    F = O.mismatch_rectangular(model.Ybus, model.V0, model.Sspec, model.busType.astype(int), model.Vset, model.slack_idx)
+    assert abs(api.mismatchInf(model, model.V0) - np.max(np.abs(F))) < 1e-14
+
+
+def test_no_cpu_fallback(has_cuda):
+    """Without a CUDA device every solve entry point must fail loudly (no CPU fallback)."""
+    if has_cuda:
+        pytest.skip("CUDA device present")
+    g = G.case14()
+    e = api.Engine(M.build_arrays(g))
+    with pytest.raises(L.SblxError) as ei:
+        e.solve_outages([[0]])
+    assert "CUDA" in str(ei.value)
+    with pytest.raises(L.SblxError):
+        e.solve_one(None)
+    e.close()
+
+
+def test_product_path_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "sparlectra.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".jl")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "sparlectra_oracle" not in txt and "import oracle" not in txt, f
