@@ -155,14 +155,15 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from sblx import api, model as M
+    from sblx import api, model as M, shard
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g, cases, per_rank, wname = workload(args, world)
-    mine = cases[rank * per_rank:(rank + 1) * per_rank]
+    lo, hi = shard.shard_range(len(cases), rank, world)
+    mine = cases[lo:hi]
     a0 = M.build_arrays(g)
     t0 = time.perf_counter()
     eng = api.Engine(a0, device=local_rank, max_slots=args.max_slots, ordering=args.ordering)
@@ -183,6 +184,7 @@ def main():
 
     # ---- device-resident arm (value)
     eng.stage_outages(optr, obr)
+    info = eng.info()
     for _ in range(args.warmup):
         eng.run_staged()
     sampler = ClockSampler(local_rank)
@@ -210,14 +212,13 @@ def main():
         class _Raw:
             __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
         mine_t = torch.as_tensor(_Raw(), device=f"cuda:{local_rank}")
-        out_t = torch.empty(nbytes * world, dtype=torch.uint8, device=f"cuda:{local_rank}")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.all_gather_into_tensor(out_t, mine_t)
+        out_t = shard.gather_records(mine_t, len(cases), world, dist)
         e1.record()
         torch.cuda.synchronize()
         gathered = e0.elapsed_time(e1)
-        conv_all = out_t.view(torch.int32).view(-1, 12)[:, 0].sum().item()
+        conv_all = out_t.clone().view(torch.int32).view(-1, 12)[:, 0].sum().item()
     else:
         conv_all = nconv
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=f"cuda:{local_rank}")

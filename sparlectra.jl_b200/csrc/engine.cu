@@ -1111,6 +1111,21 @@ int sblx_create(sblx_handle** out, int64_t n, const int64_t* colptr, const int64
     }
     if (nslack != 1 || bus_type[H.slack] != SBLX_BUS_SLACK)
       throw std::invalid_argument("sblx_create: exactly one Slack bus at slack_idx is required");
+    if (nbranch == 0) {
+      // PFModel without a branch table (solvePf of a bare model): connectivity comes from the Ybus
+      // pattern as pseudo two-ports with zero stamps (they cannot be outaged and carry no rating)
+      for (int i = 0; i < H.n; ++i)
+        for (int p = H.y_rowptr[i]; p < H.y_rowptr[i + 1]; ++p) {
+          const int j = H.y_col[p];
+          if (j > i && (H.y_val[p].x != 0.0 || H.y_val[p].y != 0.0)) {
+            H.br_from.push_back(i); H.br_to.push_back(j);
+            H.y11.push_back(make_double2(0, 0)); H.y12.push_back(make_double2(0, 0));
+            H.y21.push_back(make_double2(0, 0)); H.y22.push_back(make_double2(0, 0));
+            H.rating.push_back(std::nan("")); H.br_status.push_back(1);
+          }
+        }
+      H.nbr = (int)H.br_from.size();
+    } else {
     H.br_from.resize(nbranch); H.br_to.resize(nbranch); H.y11.resize(nbranch); H.y12.resize(nbranch);
     H.y21.resize(nbranch); H.y22.resize(nbranch); H.rating.resize(nbranch); H.br_status.resize(nbranch);
     for (int64_t k = 0; k < nbranch; ++k) {
@@ -1119,6 +1134,7 @@ int sblx_create(sblx_handle** out, int64_t n, const int64_t* colptr, const int64
       H.y21[k] = make_double2(br_y21[2 * k], br_y21[2 * k + 1]); H.y22[k] = make_double2(br_y22[2 * k], br_y22[2 * k + 1]);
       H.rating[k] = br_rating ? br_rating[k] : std::nan("");
       H.br_status[k] = br_status ? (br_status[k] != 0) : 1;
+    }
     }
     build_topology(H);
     {
