@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ordering", type=int, default=0)
+    ap.add_argument("--relax-small", type=int, default=0)
+    ap.add_argument("--relax-frac", type=float, default=0.0)
     return ap.parse_args()
 
 
@@ -166,7 +168,12 @@ def main():
     mine = cases[lo:hi]
     a0 = M.build_arrays(g)
     t0 = time.perf_counter()
-    eng = api.Engine(a0, device=local_rank, max_slots=args.max_slots, ordering=args.ordering)
+    extra = {}
+    if args.relax_small > 0:
+        extra["relax_small"] = args.relax_small
+    if args.relax_frac > 0:
+        extra["relax_zero_frac"] = args.relax_frac
+    eng = api.Engine(a0, device=local_rank, max_slots=args.max_slots, ordering=args.ordering, **extra)
     t_create = time.perf_counter() - t0
     Vb, conv, itb, resb, stb = eng.solve_one(None)
     if not conv:

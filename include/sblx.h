@@ -84,7 +84,7 @@ typedef struct sblx_options {
   int32_t device;               /* CUDA device ordinal, -1 = current [-1] */
   int32_t max_slots;            /* scenario slots resident on the GPU, 0 = auto from free memory [0] */
   int32_t ordering;             /* 0 auto, 1 minimum degree, 2 nested dissection [0] */
-  int32_t reserved0;
+  int32_t relax_small;          /* always merge a child front when the merged front has <= this many buses [28] */
   double tol;                   /* [1e-8] */
   double damp;                  /* [1.0] */
   double q_hyst_pu;             /* net.q_hyst_pu [0.0] */

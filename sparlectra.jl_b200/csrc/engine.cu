@@ -164,6 +164,7 @@ static void build_nodes_and_symbolic(HostModel& H, const sblx_options& o) {
   SymbolicOptions so;
   so.ordering = o.ordering;
   so.relax_zero_frac = o.relax_zero_frac;
+  if (o.relax_small > 0) so.relax_small = o.relax_small;
   analyze(H.m, H.jb_rowptr, H.jb_col, so, H.sym);
 }
 
@@ -226,7 +227,7 @@ static double host_selftest(const HostModel& H, uint64_t seed) {
           for (int bb = 0; bb < hc; ++bb) {
             if (a >= kc && bb >= kc) continue;
             int la = rel[a], lb = rel[bb];
-            double* d = la < w ? &T[((size_t)la * nf + lb) * 4] : &Lp[((size_t)(la - w) * w + lb) * 4];
+            double* d = la < w ? &T[((size_t)la * nf + lb) * 4] : &Lp[((size_t)lb * h + (la - w)) * 4];
             for (int z = 0; z < 4; ++z) d[z] += Cm[((size_t)a * hc + bb) * 4 + z];
           }
         for (int a = 0; a < kc; ++a) { b1[2 * rel[a]] += cv[2 * a]; b1[2 * rel[a] + 1] += cv[2 * a + 1]; }
@@ -249,8 +250,8 @@ static double host_selftest(const HostModel& H, uint64_t seed) {
           b1[2 * i + 1] -= a[2] * y0 + a[3] * y1;
         }
         for (int a = 0; a < h; ++a) {
-          const double* lv = &Lp[((size_t)a * w + p) * 4];
-          for (int c = p + 1; c < w; ++c) mm_sub(&Lp[((size_t)a * w + c) * 4], lv, &T[((size_t)p * nf + c) * 4]);
+          const double* lv = &Lp[((size_t)p * h + a) * 4];
+          for (int c = p + 1; c < w; ++c) mm_sub(&Lp[((size_t)c * h + a) * 4], lv, &T[((size_t)p * nf + c) * 4]);
         }
       }
       std::copy(T.begin(), T.end(), U.begin() + (size_t)P.u_off * 4);
@@ -260,7 +261,7 @@ static double host_selftest(const HostModel& H, uint64_t seed) {
       for (int a = 0; a < h; ++a) {
         for (int bb = 0; bb < h; ++bb) {
           double acc[4] = {0, 0, 0, 0};
-          for (int p = 0; p < w; ++p) mm_sub(acc, &Lp[((size_t)a * w + p) * 4], &T[((size_t)p * nf + w + bb) * 4]);
+          for (int p = 0; p < w; ++p) mm_sub(acc, &Lp[((size_t)p * h + a) * 4], &T[((size_t)p * nf + w + bb) * 4]);
           for (int ci = 0; ci < P.nchild; ++ci) {
             int c = S.child_list[P.child_ptr + ci];
             const Panel& Cp = S.panels[c];
@@ -272,7 +273,7 @@ static double host_selftest(const HostModel& H, uint64_t seed) {
         }
         double v0 = 0, v1 = 0;
         for (int p = 0; p < w; ++p) {
-          const double* lv = &Lp[((size_t)a * w + p) * 4];
+          const double* lv = &Lp[((size_t)p * h + a) * 4];
           v0 -= lv[0] * b1[2 * p] + lv[1] * b1[2 * p + 1];
           v1 -= lv[2] * b1[2 * p] + lv[3] * b1[2 * p + 1];
         }
@@ -447,8 +448,8 @@ static void upload_model(sblx_handle* h) {
   h->d_rel_ptr.upload(rp, s);
   h->d_inv_ptr.upload(ip, s);
   // launch groups: per level, panels sorted by size class
-  auto front_class = [](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 72 * 1024 ? 2 : 3; };
-  static const int front_nt[4] = {32, 64, 128, 256};
+  auto front_class = [](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 72 * 1024 ? 2 : bytes <= 110 * 1024 ? 3 : 4; };
+  static const int front_nt[5] = {32, 64, 128, 256, 512};
   std::vector<int> lp;
   h->front_groups.assign(S.nlevels, {});
   h->solve_groups.assign(S.nlevels, {});
@@ -481,7 +482,8 @@ static void upload_model(sblx_handle* h) {
   CK(cudaFuncSetAttribute(k_front<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024));
   CK(cudaFuncSetAttribute(k_front<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
   CK(cudaFuncSetAttribute(k_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-  CK(cudaFuncSetAttribute(k_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CK(cudaFuncSetAttribute(k_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  CK(cudaFuncSetAttribute(k_front<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CK(cudaFuncSetAttribute(k_backsolve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(k_backsolve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(k_backsolve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -902,7 +904,8 @@ static void run_staged(sblx_handle* h) {
             case 32: launch_front<32>(h, g, nstep); break;
             case 64: launch_front<64>(h, g, nstep); break;
             case 128: launch_front<128>(h, g, nstep); break;
-            default: launch_front<256>(h, g, nstep); break;
+            case 256: launch_front<256>(h, g, nstep); break;
+            default: launch_front<512>(h, g, nstep); break;
           }
           st.launches++;
           st.factor_launches++;
@@ -1040,6 +1043,7 @@ void sblx_default_options(sblx_options* o) {
   o->device = -1;
   o->max_slots = 0;
   o->ordering = 0;
+  o->relax_small = 28;
   o->tol = 1e-8;
   o->damp = 1.0;
   o->q_hyst_pu = 0.0;
@@ -1355,7 +1359,8 @@ int sblx_debug_newton_step(sblx_handle* h, int64_t nout, const int32_t* outage_b
         case 32: launch_front<32>(h, g, 1); break;
         case 64: launch_front<64>(h, g, 1); break;
         case 128: launch_front<128>(h, g, 1); break;
-        default: launch_front<256>(h, g, 1); break;
+        case 256: launch_front<256>(h, g, 1); break;
+        default: launch_front<512>(h, g, 1); break;
       }
     }
   for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)

@@ -494,16 +494,16 @@ __device__ __forceinline__ bool inv2x2(double2 r0, double2 r1, double2& i0, doub
   i1 = make_double2(-c * s, a * s);
   return ok;
 }
-// t -= a * u for 2x2 blocks (rows as double2)
+// t -= a * u for 2x2 blocks (rows as double2): 8 DFMA, no separate multiplies/adds
 __device__ __forceinline__ void bmsub(double2& t0, double2& t1, double2 a0, double2 a1, double2 u0, double2 u1) {
-  t0.x -= a0.x * u0.x + a0.y * u1.x;
-  t0.y -= a0.x * u0.y + a0.y * u1.y;
-  t1.x -= a1.x * u0.x + a1.y * u1.x;
-  t1.y -= a1.x * u0.y + a1.y * u1.y;
+  t0.x = fma(-a0.x, u0.x, t0.x); t0.x = fma(-a0.y, u1.x, t0.x);
+  t0.y = fma(-a0.x, u0.y, t0.y); t0.y = fma(-a0.y, u1.y, t0.y);
+  t1.x = fma(-a1.x, u0.x, t1.x); t1.x = fma(-a1.y, u1.x, t1.x);
+  t1.y = fma(-a1.x, u0.y, t1.y); t1.y = fma(-a1.y, u1.y, t1.y);
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
   extern __shared__ double2 sm2[];
   const int panel = panel_ids[blockIdx.x];
   if ((int)blockIdx.y >= L.counts[2]) return;
@@ -511,6 +511,8 @@ __global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, cons
   const PanelDev P = M.panels[panel];
   const int w = P.w, h = P.h, nf = w + h;
   const int tid = threadIdx.x;
+  // T0/T1: pivot rows [w][nf] (block row 0 / block row 1 planes); L0/L1: structure rows x pivot columns stored
+  // PIVOT-MAJOR [w][h] so that consecutive threads (consecutive structure rows) hit consecutive 16 B words.
   double2* T0 = sm2;
   double2* T1 = T0 + w * nf;
   double2* L0 = T1 + w * nf;
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, cons
   double2* b1 = L1 + h * w;
   const int nT = w * nf, nL = h * w;
   {
-    const int tot = 2 * nT + 2 * nL + w;
+    const int tot = 2 * nT + 2 * nL + 3 * w;
     for (int i = tid; i < tot; i += NT) sm2[i] = make_double2(0.0, 0.0);
   }
   __syncthreads();
@@ -536,73 +538,131 @@ __global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, cons
   }
   __syncthreads();
   double* Cs = A.C + (size_t)slot * M.c_blocks * 4;
-  // ---- extend-add of the children's update matrices into the pivot rows / columns
-  for (int ci = 0; ci < P.nchild; ++ci) {
-    const int c = M.child_list[P.child_ptr + ci];
-    const PanelDev Cp = M.panels[c];
-    const int hc = Cp.h, kc = M.kpiv[c];
-    const int* rel = M.rel + M.rel_ptr[c];
-    const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
-    const double2* cv = Cm + 2 * (size_t)hc * hc;
-    const int n1 = kc * hc, n2 = (hc - kc) * kc;
-    for (int idx = tid; idx < n1 + n2; idx += NT) {
-      int a, b;
-      if (idx < n1) { a = idx / hc; b = idx - a * hc; }
-      else { const int t = idx - n1; a = kc + t / kc; b = t - (a - kc) * kc; }
-      const int la = rel[a], lb = rel[b];
-      const double2 s0 = Cm[2 * (a * hc + b)], s1 = Cm[2 * (a * hc + b) + 1];
-      if (la < w) {
-        const int d = la * nf + lb;
-        T0[d] = cadd(T0[d], s0); T1[d] = cadd(T1[d], s1);
-      } else {
-        const int d = (la - w) * w + lb;
-        L0[d] = cadd(L0[d], s0); L1[d] = cadd(L1[d], s1);
+  // ---- extend-add of the children's update matrices into the pivot rows / columns (no integer
+  // division: warps stride over rows, lanes over columns; 32 B blocks are whole DRAM sectors)
+  {
+    const int lane = tid & 31, warp = tid >> 5, nwarp = NT / 32;
+    for (int ci = 0; ci < P.nchild; ++ci) {
+      const int c = M.child_list[P.child_ptr + ci];
+      const PanelDev Cp = M.panels[c];
+      const int hc = Cp.h, kc = M.kpiv[c];
+      const int* rel = M.rel + M.rel_ptr[c];
+      const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
+      const double2* cv = Cm + 2 * (size_t)hc * hc;
+      // rows that are pivots of this front: the whole child row
+      for (int a = warp; a < kc; a += nwarp) {
+        const int la = rel[a];
+        const double2* row = Cm + 2 * (size_t)a * hc;
+        for (int b0 = lane; b0 < hc; b0 += 64) {
+          const int b1i = b0 + 32;
+          const bool v1 = b1i < hc;
+          const int lb0 = rel[b0], lb1 = v1 ? rel[b1i] : 0;
+          const double2 x0 = row[2 * b0], x1 = row[2 * b0 + 1];
+          double2 y0 = make_double2(0.0, 0.0), y1 = y0;
+          if (v1) { y0 = row[2 * b1i]; y1 = row[2 * b1i + 1]; }
+          const int d0 = la * nf + lb0;
+          T0[d0] = cadd(T0[d0], x0); T1[d0] = cadd(T1[d0], x1);
+          if (v1) { const int d1 = la * nf + lb1; T0[d1] = cadd(T0[d1], y0); T1[d1] = cadd(T1[d1], y1); }
+        }
       }
+      // structure rows x pivot columns
+      for (int b = warp; b < kc; b += nwarp) {
+        const int lb = rel[b];
+        for (int a0 = kc + lane; a0 < hc; a0 += 64) {
+          const int a1 = a0 + 32;
+          const bool v1 = a1 < hc;
+          const int la0 = rel[a0] - w, la1 = v1 ? rel[a1] - w : 0;
+          const double2 x0 = Cm[2 * ((size_t)a0 * hc + b)], x1 = Cm[2 * ((size_t)a0 * hc + b) + 1];
+          double2 y0 = make_double2(0.0, 0.0), y1 = y0;
+          if (v1) { y0 = Cm[2 * ((size_t)a1 * hc + b)]; y1 = Cm[2 * ((size_t)a1 * hc + b) + 1]; }
+          const int d0 = lb * h + la0;
+          L0[d0] = cadd(L0[d0], x0); L1[d0] = cadd(L1[d0], x1);
+          if (v1) { const int d1 = lb * h + la1; L0[d1] = cadd(L0[d1], y0); L1[d1] = cadd(L1[d1], y1); }
+        }
+      }
+      for (int a = tid; a < kc; a += NT) b1[rel[a]] = cadd(b1[rel[a]], cv[a]);
+      __syncthreads();
     }
-    for (int a = tid; a < kc; a += NT) b1[rel[a]] = cadd(b1[rel[a]], cv[a]);
-    __syncthreads();
   }
-  // ---- right-looking factorisation of the w pivots inside the panel
-  bool sing = false;
-  for (int p = 0; p < w; ++p) {
-    double2 d0, d1;
-    const bool ok = inv2x2(T0[p * nf + p], T1[p * nf + p], d0, d1);
-    sing |= !ok;          // (the pivot block itself is never rescaled, so no barrier is needed here)
-    for (int c = p + tid; c < nf + 1; c += NT) {
-      if (c == p) continue;
-      if (c == nf) {       // rhs entry
-        const double2 v = b1[p];
-        b1[p] = make_double2(d0.x * v.x + d0.y * v.y, d1.x * v.x + d1.y * v.y);
-      } else {
-        const double2 u0 = T0[p * nf + c], u1 = T1[p * nf + c];
-        T0[p * nf + c] = make_double2(d0.x * u0.x + d0.y * u1.x, d0.x * u0.y + d0.y * u1.y);
-        T1[p * nf + c] = make_double2(d1.x * u0.x + d1.y * u1.x, d1.x * u0.y + d1.y * u1.y);
+  // ---- panel factorisation, step 1: the w x w pivot block (and the pivots' rhs) by warp 0.
+  // Rows are pre-scaled by the inverse 2x2 pivot (U' = D^-1 U), multipliers stay unscaled.
+  double2* Dv0 = b1 + w;
+  double2* Dv1 = Dv0 + w;
+  if (tid < 32) {
+    const int lane = tid;
+    const int li = lane >> 3, lc = lane & 7;        // 4 rows x 8 columns of lanes
+    bool sing = false;
+    for (int p = 0; p < w; ++p) {
+      double2 d0, d1;
+      sing |= !inv2x2(T0[p * nf + p], T1[p * nf + p], d0, d1);
+      __syncwarp();
+      for (int c = p + 1 + lane; c <= w; c += 32) {
+        if (c == w) {
+          const double2 v = b1[p];
+          b1[p] = make_double2(d0.x * v.x + d0.y * v.y, d1.x * v.x + d1.y * v.y);
+        } else {
+          const double2 u0 = T0[p * nf + c], u1 = T1[p * nf + c];
+          T0[p * nf + c] = make_double2(d0.x * u0.x + d0.y * u1.x, d0.x * u0.y + d0.y * u1.y);
+          T1[p * nf + c] = make_double2(d1.x * u0.x + d1.y * u1.x, d1.x * u0.y + d1.y * u1.y);
+        }
       }
-    }
-    __syncthreads();
-    const int nr = w - p - 1, nc = nf - p - 1;
-    const int n1 = nr * nc, n2 = h * nr;
-    for (int idx = tid; idx < n1 + n2 + nr; idx += NT) {
-      if (idx < n1) {
-        const int i = p + 1 + idx / nc, c = p + 1 + idx % nc;
-        bmsub(T0[i * nf + c], T1[i * nf + c], T0[i * nf + p], T1[i * nf + p], T0[p * nf + c], T1[p * nf + c]);
-      } else if (idx < n1 + n2) {
-        const int t = idx - n1;
-        const int a = t / nr, c = p + 1 + t % nr;
-        bmsub(L0[a * w + c], L1[a * w + c], L0[a * w + p], L1[a * w + p], T0[p * nf + c], T1[p * nf + c]);
-      } else {
-        const int i = p + 1 + (idx - n1 - n2);
-        const double2 y = b1[p];
+      if (lane == 0) { Dv0[p] = d0; Dv1[p] = d1; }
+      __syncwarp();
+      for (int i = p + 1 + li; i < w; i += 4) {
         const double2 a0 = T0[i * nf + p], a1 = T1[i * nf + p];
-        double2 v = b1[i];
-        v.x -= a0.x * y.x + a0.y * y.y;
-        v.y -= a1.x * y.x + a1.y * y.y;
-        b1[i] = v;
+        for (int c = p + 1 + lc; c <= w; c += 8) {
+          if (c == w) {
+            const double2 y = b1[p];
+            double2 v = b1[i];
+            v.x = fma(-a0.x, y.x, v.x); v.x = fma(-a0.y, y.y, v.x);
+            v.y = fma(-a1.x, y.x, v.y); v.y = fma(-a1.y, y.y, v.y);
+            b1[i] = v;
+          } else {
+            bmsub(T0[i * nf + c], T1[i * nf + c], a0, a1, T0[p * nf + c], T1[p * nf + c]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (sing && lane == 0) atomicOr(&A.singular[slot], 1);
+  }
+  __syncthreads();
+  // ---- step 2: independent tasks, no barriers: U'12 columns (forward substitution with the
+  // multipliers of the pivot block) and L21 rows (substitution with the scaled pivot rows)
+  {
+    const int hpad = (h + 31) & ~31;
+    for (int t = tid; t < 2 * hpad; t += NT) {
+      if (t < hpad) {
+        const int b = t;
+        if (b < h) {
+          double2* c0 = T0 + w + b;
+          double2* c1 = T1 + w + b;
+          for (int p = 0; p < w; ++p) {
+            double2 x0 = c0[p * nf], x1 = c1[p * nf];
+            const double2* m0 = T0 + p * nf;
+            const double2* m1 = T1 + p * nf;
+            for (int q = 0; q < p; ++q) bmsub(x0, x1, m0[q], m1[q], c0[q * nf], c1[q * nf]);
+            const double2 d0 = Dv0[p], d1 = Dv1[p];
+            c0[p * nf] = make_double2(d0.x * x0.x + d0.y * x1.x, d0.x * x0.y + d0.y * x1.y);
+            c1[p * nf] = make_double2(d1.x * x0.x + d1.y * x1.x, d1.x * x0.y + d1.y * x1.y);
+          }
+        }
+      } else {
+        const int a = t - hpad;
+        if (a < h) {
+          double2* r0 = L0 + a;
+          double2* r1 = L1 + a;
+          for (int p = 1; p < w; ++p) {
+            double2 x0 = r0[p * h], x1 = r1[p * h];
+            for (int q = 0; q < p; ++q) bmsub(x0, x1, r0[q * h], r1[q * h], T0[q * nf + p], T1[q * nf + p]);
+            r0[p * h] = x0;
+            r1[p * h] = x1;
+          }
+        }
       }
     }
-    __syncthreads();
   }
-  if (sing && tid == 0) atomicOr(&A.singular[slot], 1);
+  __syncthreads();
   // ---- store U' panel and y'
   {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
@@ -610,9 +670,79 @@ __global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, cons
     double2* y = A.yv + (size_t)slot * M.m + P.first;
     for (int p = tid; p < w; p += NT) y[p] = b1[p];
   }
-  // ---- Schur complement straight to HBM: C = gather(children) - L * U'   (2x2-block register tiles)
-  if (h > 0) {
-    double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
+  if (h == 0) return;
+  double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
+  // ---- Schur complement straight to HBM: C = gather(children) - L * U'
+  if (NT >= 128) {
+    // warp-level work items: 4 structure rows x 64 structure columns; lane l owns columns (cg*64 + l) and
+    // (cg*64 + 32 + l): L loads are warp broadcasts, U' loads are consecutive 16 B words (no bank conflicts),
+    // 32 accumulators per thread (64 DFMA per 12 LDS.128).
+    const int lane = tid & 31, warp = tid >> 5, nwarp = NT / 32;
+    const int ncg = (h + 63) >> 6, nrg = (h + 3) >> 2;
+    for (int item = warp; item < nrg * ncg; item += nwarp) {
+      const int rg = item / ncg, cg = item - rg * ncg;
+      const int a0 = rg * 4;
+      const int bA = cg * 64 + lane, bB = bA + 32;
+      const bool vA = bA < h, vB = bB < h;
+      const int cA = vA ? bA : h - 1, cB = vB ? bB : h - 1;
+      int ar[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ar[i] = min(a0 + i, h - 1);
+      double2 acc[4][2][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc[i][j][0] = make_double2(0.0, 0.0); acc[i][j][1] = make_double2(0.0, 0.0); }
+      const double2* u0p = T0 + w + cA;
+      const double2* u1p = T1 + w + cA;
+      const int dB = cB - cA;
+#pragma unroll 2
+      for (int p = 0; p < w; ++p) {
+        const double2 ua0 = u0p[p * nf], ua1 = u1p[p * nf];
+        const double2 ub0 = u0p[p * nf + dB], ub1 = u1p[p * nf + dB];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double2 l0 = L0[p * h + ar[i]], l1 = L1[p * h + ar[i]];
+          bmsub(acc[i][0][0], acc[i][0][1], l0, l1, ua0, ua1);
+          bmsub(acc[i][1][0], acc[i][1][1], l0, l1, ub0, ub1);
+        }
+      }
+      for (int ci = 0; ci < P.nchild; ++ci) {
+        const int c = M.child_list[P.child_ptr + ci];
+        const PanelDev Cp = M.panels[c];
+        const int hc = Cp.h;
+        const int* inv = M.inv + M.inv_ptr[P.child_ptr + ci];
+        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
+        const int ibA = vA ? inv[bA] : -1, ibB = vB ? inv[bB] : -1;
+        // all (predicated) loads are issued before any accumulation: 16 independent 16 B loads in flight
+        double2 g[4][2][2];
+        int ia[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ia[i] = (a0 + i < h) ? inv[a0 + i] : -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool okA = ia[i] >= 0 && ibA >= 0, okB = ia[i] >= 0 && ibB >= 0;
+          const double2* spA = Cm + 2 * ((size_t)(okA ? ia[i] : 0) * hc + (okA ? ibA : 0));
+          const double2* spB = Cm + 2 * ((size_t)(okB ? ia[i] : 0) * hc + (okB ? ibB : 0));
+          const double2 z = make_double2(0.0, 0.0);
+          g[i][0][0] = okA ? spA[0] : z; g[i][0][1] = okA ? spA[1] : z;
+          g[i][1][0] = okB ? spB[0] : z; g[i][1][1] = okB ? spB[1] : z;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][0][0] = cadd(acc[i][0][0], g[i][0][0]); acc[i][0][1] = cadd(acc[i][0][1], g[i][0][1]);
+          acc[i][1][0] = cadd(acc[i][1][0], g[i][1][0]); acc[i][1][1] = cadd(acc[i][1][1], g[i][1][1]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (a0 + i >= h) break;
+        if (vA) { Co[2 * ((a0 + i) * h + bA)] = acc[i][0][0]; Co[2 * ((a0 + i) * h + bA) + 1] = acc[i][0][1]; }
+        if (vB) { Co[2 * ((a0 + i) * h + bB)] = acc[i][1][0]; Co[2 * ((a0 + i) * h + bB) + 1] = acc[i][1][1]; }
+      }
+    }
+  } else {
+    // small fronts: one 2x2-block register tile per thread
     const int th = (h + 1) >> 1;
     for (int tile = tid; tile < th * th; tile += NT) {
       const int a0 = (tile / th) * 2, b0 = (tile % th) * 2;
@@ -624,8 +754,8 @@ __global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, cons
         for (int y = 0; y < 2; ++y) { acc[x][y][0] = make_double2(0.0, 0.0); acc[x][y][1] = make_double2(0.0, 0.0); }
       const int a1i = va ? a0 + 1 : a0, b1i = vb ? b0 + 1 : b0;
       for (int p = 0; p < w; ++p) {
-        const double2 la0 = L0[a0 * w + p], la1 = L1[a0 * w + p];
-        const double2 lb0 = L0[a1i * w + p], lb1 = L1[a1i * w + p];
+        const double2 la0 = L0[p * h + a0], la1 = L1[p * h + a0];
+        const double2 lb0 = L0[p * h + a1i], lb1 = L1[p * h + a1i];
         const double2 ua0 = T0[p * nf + w + b0], ua1 = T1[p * nf + w + b0];
         const double2 ub0 = T0[p * nf + w + b1i], ub1 = T1[p * nf + w + b1i];
         bmsub(acc[0][0][0], acc[0][0][1], la0, la1, ua0, ua1);
@@ -641,10 +771,10 @@ __global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, cons
         const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
         const int ia0 = inv[a0], ia1 = va ? inv[a0 + 1] : -1;
         const int ib0 = inv[b0], ib1 = vb ? inv[b0 + 1] : -1;
-        if (ia0 >= 0 && ib0 >= 0) { const double2* s = Cm + 2 * (ia0 * hc + ib0); acc[0][0][0] = cadd(acc[0][0][0], s[0]); acc[0][0][1] = cadd(acc[0][0][1], s[1]); }
-        if (ia0 >= 0 && ib1 >= 0) { const double2* s = Cm + 2 * (ia0 * hc + ib1); acc[0][1][0] = cadd(acc[0][1][0], s[0]); acc[0][1][1] = cadd(acc[0][1][1], s[1]); }
-        if (ia1 >= 0 && ib0 >= 0) { const double2* s = Cm + 2 * (ia1 * hc + ib0); acc[1][0][0] = cadd(acc[1][0][0], s[0]); acc[1][0][1] = cadd(acc[1][0][1], s[1]); }
-        if (ia1 >= 0 && ib1 >= 0) { const double2* s = Cm + 2 * (ia1 * hc + ib1); acc[1][1][0] = cadd(acc[1][1][0], s[0]); acc[1][1][1] = cadd(acc[1][1][1], s[1]); }
+        if (ia0 >= 0 && ib0 >= 0) { const double2* sp = Cm + 2 * (ia0 * hc + ib0); acc[0][0][0] = cadd(acc[0][0][0], sp[0]); acc[0][0][1] = cadd(acc[0][0][1], sp[1]); }
+        if (ia0 >= 0 && ib1 >= 0) { const double2* sp = Cm + 2 * (ia0 * hc + ib1); acc[0][1][0] = cadd(acc[0][1][0], sp[0]); acc[0][1][1] = cadd(acc[0][1][1], sp[1]); }
+        if (ia1 >= 0 && ib0 >= 0) { const double2* sp = Cm + 2 * (ia1 * hc + ib0); acc[1][0][0] = cadd(acc[1][0][0], sp[0]); acc[1][0][1] = cadd(acc[1][0][1], sp[1]); }
+        if (ia1 >= 0 && ib1 >= 0) { const double2* sp = Cm + 2 * (ia1 * hc + ib1); acc[1][1][0] = cadd(acc[1][1][0], sp[0]); acc[1][1][1] = cadd(acc[1][1][1], sp[1]); }
       }
       Co[2 * (a0 * h + b0)] = acc[0][0][0]; Co[2 * (a0 * h + b0) + 1] = acc[0][0][1];
       if (vb) { Co[2 * (a0 * h + b0 + 1)] = acc[0][1][0]; Co[2 * (a0 * h + b0 + 1) + 1] = acc[0][1][1]; }
@@ -653,26 +783,26 @@ __global__ void __launch_bounds__(NT) k_front(DevModel M, Slots A, Lists L, cons
         if (vb) { Co[2 * ((a0 + 1) * h + b0 + 1)] = acc[1][1][0]; Co[2 * ((a0 + 1) * h + b0 + 1) + 1] = acc[1][1][1]; }
       }
     }
-    // update vector: cv[a] = gather(children) - L[a][:] y'
-    double2* cvo = Co + 2 * (size_t)h * h;
-    for (int a = tid; a < h; a += NT) {
-      double2 v = make_double2(0.0, 0.0);
-      for (int p = 0; p < w; ++p) {
-        const double2 l0 = L0[a * w + p], l1 = L1[a * w + p], y = b1[p];
-        v.x -= l0.x * y.x + l0.y * y.y;
-        v.y -= l1.x * y.x + l1.y * y.y;
-      }
-      for (int ci = 0; ci < P.nchild; ++ci) {
-        const int c = M.child_list[P.child_ptr + ci];
-        const PanelDev Cp = M.panels[c];
-        const int ia = M.inv[M.inv_ptr[P.child_ptr + ci] + a];
-        if (ia >= 0) {
-          const double2* cvc = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4) + 2 * (size_t)Cp.h * Cp.h;
-          v = cadd(v, cvc[ia]);
-        }
-      }
-      cvo[a] = v;
+  }
+  // ---- update vector: cv[a] = gather(children) - L[a][:] y'
+  double2* cvo = Co + 2 * (size_t)h * h;
+  for (int a = tid; a < h; a += NT) {
+    double2 v = make_double2(0.0, 0.0);
+    for (int p = 0; p < w; ++p) {
+      const double2 l0 = L0[p * h + a], l1 = L1[p * h + a], y = b1[p];
+      v.x -= l0.x * y.x + l0.y * y.y;
+      v.y -= l1.x * y.x + l1.y * y.y;
     }
+    for (int ci = 0; ci < P.nchild; ++ci) {
+      const int c = M.child_list[P.child_ptr + ci];
+      const PanelDev Cp = M.panels[c];
+      const int ia = M.inv[M.inv_ptr[P.child_ptr + ci] + a];
+      if (ia >= 0) {
+        const double2* cvc = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4) + 2 * (size_t)Cp.h * Cp.h;
+        v = cadd(v, cvc[ia]);
+      }
+    }
+    cvo[a] = v;
   }
 }
 

@@ -501,7 +501,7 @@ static void build_from_order(int m, const std::vector<int64_t>& rowptr, const st
         int li = local_index(P, fi), lj = local_index(P, fj);
         if (li < 0 || lj < 0) throw std::runtime_error("sblx symbolic: Jacobian block outside its front");
         int nf = P.w + P.h;
-        int dst = (li < P.w) ? (li * nf + lj) : (P.w * nf + (li - P.w) * P.w + lj);
+        int dst = (li < P.w) ? (li * nf + lj) : (P.w * nf + lj * P.h + (li - P.w));   // structure rows: pivot-major [w][h]
         lists[owner].push_back({(int)k, dst});
       }
     }
@@ -655,6 +655,7 @@ int main(int argc, char** argv) {
   opt.ordering = ordering;
   if (argc > 4) opt.max_panel_width = atoi(argv[4]);
   if (argc > 5) opt.relax_zero_frac = atof(argv[5]);
+  if (argc > 6) opt.relax_small = atoi(argv[6]);
   sblx::Symbolic S;
   sblx::analyze(m, rp, ci, opt, S);
   printf("%s\n", S.summary().c_str());
@@ -664,7 +665,7 @@ int main(int argc, char** argv) {
   double cread = 0;
   for (auto& P : S.panels) {
     int b = sblx::panel_smem_bytes(P.w, P.h);
-    int k = b <= 8192 ? 0 : b <= 49152 ? 1 : b <= 110000 ? 2 : 3;
+    int k = b <= 6144 ? 0 : b <= 24576 ? 1 : b <= 73728 ? 2 : 3;
     double w = P.w, h = P.h, nf = w + h, o = h * h * w;
     for (int p = 0; p < P.w; ++p) o += (w - p - 1) * (nf - p - 1) + h * (w - p - 1);
     ops_by[k] += o;

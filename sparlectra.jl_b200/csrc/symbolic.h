@@ -78,6 +78,6 @@ void analyze(int m, const std::vector<int64_t>& rowptr, const std::vector<int>& 
              Symbolic& out);
 
 // shared-memory bytes a panel needs in the factor kernel
-inline int panel_smem_bytes(int w, int h) { return ((w * (w + h) + h * w) * 4 + 2 * w + 8) * 8; }
+inline int panel_smem_bytes(int w, int h) { return ((w * (w + h) + h * w) * 4 + 6 * w + 8) * 8; }
 
 }  // namespace sblx
