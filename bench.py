@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--ordering", type=int, default=0)
     ap.add_argument("--relax-small", type=int, default=0)
     ap.add_argument("--relax-frac", type=float, default=0.0)
+    ap.add_argument("--panel-kb", type=float, default=0.0)
     return ap.parse_args()
 
 
@@ -173,6 +174,8 @@ def main():
         extra["relax_small"] = args.relax_small
     if args.relax_frac > 0:
         extra["relax_zero_frac"] = args.relax_frac
+    if args.panel_kb > 0:
+        extra["panel_smem_kb"] = args.panel_kb
     eng = api.Engine(a0, device=local_rank, max_slots=args.max_slots, ordering=args.ordering, **extra)
     t_create = time.perf_counter() - t0
     Vb, conv, itb, resb, stb = eng.solve_one(None)

@@ -93,6 +93,7 @@ typedef struct sblx_options {
   double base_mva;              /* [100.0] (loading in percent of sn_MVA) */
   double mem_fraction;          /* share of free device memory the auto slot count may use [0.6] */
   double relax_zero_frac;       /* supernode amalgamation threshold [0.08] */
+  double panel_smem_kb;         /* shared-memory budget of one front panel in KB (<= 200) [200] */
 } sblx_options;
 
 /* Caller-allocated result arrays (any may be NULL). B = number of scenarios, n = buses. */

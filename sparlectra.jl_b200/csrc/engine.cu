@@ -165,7 +165,9 @@ static void build_nodes_and_symbolic(HostModel& H, const sblx_options& o) {
   so.ordering = o.ordering;
   so.relax_zero_frac = o.relax_zero_frac;
   if (o.relax_small > 0) so.relax_small = o.relax_small;
+  if (o.panel_smem_kb >= 4.0 && o.panel_smem_kb <= 200.0) so.smem_budget_bytes = (int)(o.panel_smem_kb * 1024);
   analyze(H.m, H.jb_rowptr, H.jb_col, so, H.sym);
+  if (H.sym.max_w > 16) throw std::runtime_error("sblx: panel wider than 16 pivots");
 }
 
 // Plain C++ walk over the same panels / index maps as k_front + k_backsolve (symbolic self-test).
@@ -354,7 +356,8 @@ struct sblx_handle {
   DevBuf<unsigned char> d_type0, d_lock, d_br_status;
   DevBuf<int> d_br_from, d_br_to;
   DevBuf<PanelDev> d_panels;
-  DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels;
+  DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels, d_ing_ptr, d_ing_src, d_vec_ptr, d_vec_src;
+  DevBuf<ChildDev> d_childdev;
   DevBuf<long long> d_rel_ptr, d_inv_ptr;
   std::vector<std::vector<LaunchGroup>> front_groups;   // per level
   std::vector<std::vector<LaunchGroup>> solve_groups;
@@ -434,7 +437,7 @@ static void upload_model(sblx_handle* h) {
   std::vector<PanelDev> pd(S.panels.size());
   for (size_t i = 0; i < pd.size(); ++i) {
     const Panel& P = S.panels[i];
-    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.asm_ptr, (int)P.asm_cnt, (long long)P.u_off, (long long)P.c_off};
+    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.ing_base, 0, (long long)P.u_off, (long long)P.c_off};
   }
   h->d_panels.upload(pd, s);
   h->d_struct.upload(S.struct_nodes, s);
@@ -444,6 +447,18 @@ static void upload_model(sblx_handle* h) {
   h->d_inv.upload(S.inv, s);
   h->d_asm_src.upload(S.asm_src, s);
   h->d_asm_dst.upload(S.asm_dst, s);
+  h->d_ing_ptr.upload(S.ing_ptr, s);
+  h->d_ing_src.upload(S.ing_src, s);
+  h->d_vec_ptr.upload(S.vec_ptr, s);
+  h->d_vec_src.upload(S.vec_src, s);
+  {
+    std::vector<ChildDev> cd(S.child_list.size());
+    for (size_t k = 0; k < cd.size(); ++k) {
+      const Panel& C = S.panels[S.child_list[k]];
+      cd[k] = ChildDev{(long long)C.c_off, C.h, (int)S.inv_ptr[k]};
+    }
+    h->d_childdev.upload(cd, s);
+  }
   std::vector<long long> rp(S.rel_ptr.begin(), S.rel_ptr.end()), ip(S.inv_ptr.begin(), S.inv_ptr.end());
   h->d_rel_ptr.upload(rp, s);
   h->d_inv_ptr.upload(ip, s);
@@ -501,6 +516,8 @@ static void upload_model(sblx_handle* h) {
   M.panels = h->d_panels.p; M.struct_nodes = h->d_struct.p; M.child_list = h->d_child.p; M.rel = h->d_rel.p;
   M.rel_ptr = h->d_rel_ptr.p; M.kpiv = h->d_kpiv.p; M.inv = h->d_inv.p; M.inv_ptr = h->d_inv_ptr.p;
   M.asm_src = h->d_asm_src.p; M.asm_dst = h->d_asm_dst.p;
+  M.ing_ptr = h->d_ing_ptr.p; M.ing_src = h->d_ing_src.p; M.vec_ptr = h->d_vec_ptr.p; M.vec_src = h->d_vec_src.p;
+  M.childdev = h->d_childdev.p;
   M.u_blocks = S.u_blocks; M.c_blocks = S.c_blocks + 2;
   const sblx_options& o = h->opt;
   M.tol = o.tol; M.damp = o.damp; M.hyst = o.q_hyst_pu; M.vm_min = o.vm_min_pu; M.vm_max = o.vm_max_pu; M.base_mva = o.base_mva;
@@ -831,6 +848,9 @@ static void run_staged(sblx_handle* h) {
   const HostModel& H = h->H;
   const int W = h->W, n = H.n, m = H.m, nnzB = (int)H.jb_col.size();
   sblx_stats& st = h->stats;
+  // per-run counters (stage-time fields host_prep_ms / h2d_* are kept)
+  st.launches = st.factor_launches = st.ticks = st.scenario_iterations = st.mismatch_evaluations = st.scenarios_solved = 0;
+  st.total_ms = st.factor_ms = st.solve_ms = st.mismatch_ms = st.jacobian_ms = st.other_ms = 0.0;
   // reset slots
   CK(cudaMemsetAsync(h->s_state.p, 0, W * sizeof(int), s));
   CK(cudaMemsetAsync(h->s_scen.p, 0xff, W * sizeof(int), s));
@@ -1052,6 +1072,7 @@ void sblx_default_options(sblx_options* o) {
   o->base_mva = 100.0;
   o->mem_fraction = 0.6;
   o->relax_zero_frac = 0.08;
+  o->panel_smem_kb = 200.0;
 }
 
 const char* sblx_last_error(const sblx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1310,6 +1331,18 @@ int sblx_solve_one(sblx_handle* h, const double* v_start, double* v_out, uint8_t
   if (residual_inf) *residual_inf = fm;
   if (status) *status = stt;
   API_END(h)
+}
+
+int sblx_debug_phase_cycles(double* out40) {
+#ifdef SBLX_PHASE_TIMING
+  unsigned long long hbuf[40];
+  if (cudaMemcpyFromSymbol(hbuf, g_phase_cycles, sizeof hbuf) != cudaSuccess) return SBLX_E_CUDA;
+  for (int i = 0; i < 40; ++i) out40[i] = (double)hbuf[i];
+  return SBLX_OK;
+#else
+  (void)out40;
+  return SBLX_E_ARG;
+#endif
 }
 
 int sblx_debug_pattern(const sblx_handle* h, int64_t* rowptr, int32_t* col) {

@@ -29,8 +29,13 @@ constexpr int T_ISO = 0, T_PQ = 1, T_PV = 2, T_SLACK = 3;
 
 struct PanelDev {
   int first, w, h, nchild;
-  int struct_ptr, child_ptr, asm_ptr, asm_cnt;
+  int struct_ptr, child_ptr, ing_base, pad0;
   long long u_off, c_off;
+};
+// per (parent, child) record used by the Schur gather
+struct ChildDev {
+  long long c_off;
+  int hc, inv_off;
 };
 
 struct DevModel {
@@ -44,6 +49,7 @@ struct DevModel {
   const double* rating; const unsigned char* br_status;
   const PanelDev* panels; const int* struct_nodes; const int* child_list; const int* rel; const long long* rel_ptr;
   const int* kpiv; const int* inv; const long long* inv_ptr; const int* asm_src; const int* asm_dst;
+  const int* ing_ptr; const int* ing_src; const int* vec_ptr; const int* vec_src; const ChildDev* childdev;
   long long u_blocks, c_blocks;
   double tol, damp, hyst, vm_min, vm_max, base_mva;
   int max_iter, qlim_enabled, qlim_start, cooldown, guard, freeze, allow_reenable;
@@ -476,6 +482,20 @@ __global__ void __launch_bounds__(256) k_jacobian(DevModel M, Slots A, Lists L) 
   out[1] = make_double2(b10, b11);
 }
 
+#ifdef SBLX_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[5][8];   // [class][phase]
+#define PHASE_MARK(ph)                                                                             \
+  do {                                                                                             \
+    if (threadIdx.x == 0) {                                                                        \
+      const long long now_ = clock64();                                                            \
+      atomicAdd(&g_phase_cycles[NT == 32 ? 0 : NT == 64 ? 1 : NT == 128 ? 2 : NT == 256 ? 3 : 4][ph], (unsigned long long)(now_ - tmark_)); \
+      tmark_ = now_;                                                                               \
+    }                                                                                              \
+  } while (0)
+#else
+#define PHASE_MARK(ph)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // K3: multifrontal panel factorisation, one CTA per (front, scenario).
 // shared memory (double2 = one block row): T0/T1 [w][nf] pivot rows, L0/L1 [h][w] structure
@@ -511,6 +531,9 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
   const PanelDev P = M.panels[panel];
   const int w = P.w, h = P.h, nf = w + h;
   const int tid = threadIdx.x;
+#ifdef SBLX_PHASE_TIMING
+  long long tmark_ = clock64();
+#endif
   // T0/T1: pivot rows [w][nf] (block row 0 / block row 1 planes); L0/L1: structure rows x pivot columns stored
   // PIVOT-MAJOR [w][h] so that consecutive threads (consecutive structure rows) hit consecutive 16 B words.
   double2* T0 = sm2;
@@ -519,118 +542,125 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
   double2* L1 = L0 + h * w;
   double2* b1 = L1 + h * w;
   const int nT = w * nf, nL = h * w;
-  {
-    const int tot = 2 * nT + 2 * nL + 3 * w;
-    for (int i = tid; i < tot; i += NT) sm2[i] = make_double2(0.0, 0.0);
-  }
-  __syncthreads();
-  // ---- original Jacobian blocks of this front
+  double* Cs = A.C + (size_t)slot * M.c_blocks * 4;
+  // ---- gather-style ingest: every panel block sums its sources (its Jacobian block, then the matching
+  // blocks of the children's update matrices, in child order) and is written to shared memory once.
   {
     const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
-    for (int k = tid; k < P.asm_cnt; k += NT) {
-      const int src = M.asm_src[P.asm_ptr + k], dst = M.asm_dst[P.asm_ptr + k];
-      const double2 r0 = Jv[2 * src], r1 = Jv[2 * src + 1];
-      if (dst < nT) { T0[dst] = r0; T1[dst] = r1; }
-      else { L0[dst - nT] = r0; L1[dst - nT] = r1; }
+    const double2* Ca = reinterpret_cast<const double2*>(Cs);
+    const int* iptr = M.ing_ptr + P.ing_base;
+    const int* isrc = M.ing_src;
+    const int nblk = nT + nL;
+    for (int k0 = tid; k0 < nblk; k0 += 2 * NT) {
+      const int k1 = k0 + NT;
+      const bool v1 = k1 < nblk;
+      const int s0 = iptr[k0], e0 = iptr[k0 + 1];
+      const int s1 = v1 ? iptr[k1] : 0, e1 = v1 ? iptr[k1 + 1] : 0;
+      double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
+      int q0 = s0, q1 = s1;
+      while (q0 < e0 || q1 < e1) {           // the two blocks' source loads are interleaved (independent)
+        double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1v = a0;
+        if (q0 < e0) {
+          const int sidx = isrc[q0++];
+          const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+          a0 = ptr[0]; a1 = ptr[1];
+        }
+        if (q1 < e1) {
+          const int sidx = isrc[q1++];
+          const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+          b0 = ptr[0]; b1v = ptr[1];
+        }
+        x0 = cadd(x0, a0); x1 = cadd(x1, a1); y0 = cadd(y0, b0); y1 = cadd(y1, b1v);
+      }
+      if (k0 < nT) { T0[k0] = x0; T1[k0] = x1; } else { L0[k0 - nT] = x0; L1[k0 - nT] = x1; }
+      if (v1) { if (k1 < nT) { T0[k1] = y0; T1[k1] = y1; } else { L0[k1 - nT] = y0; L1[k1 - nT] = y1; } }
     }
     const double2* r = A.rhs + (size_t)slot * M.m + P.first;
-    for (int p = tid; p < w; p += NT) b1[p] = r[p];
-  }
-  __syncthreads();
-  double* Cs = A.C + (size_t)slot * M.c_blocks * 4;
-  // ---- extend-add of the children's update matrices into the pivot rows / columns (no integer
-  // division: warps stride over rows, lanes over columns; 32 B blocks are whole DRAM sectors)
-  {
-    const int lane = tid & 31, warp = tid >> 5, nwarp = NT / 32;
-    for (int ci = 0; ci < P.nchild; ++ci) {
-      const int c = M.child_list[P.child_ptr + ci];
-      const PanelDev Cp = M.panels[c];
-      const int hc = Cp.h, kc = M.kpiv[c];
-      const int* rel = M.rel + M.rel_ptr[c];
-      const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
-      const double2* cv = Cm + 2 * (size_t)hc * hc;
-      // rows that are pivots of this front: the whole child row
-      for (int a = warp; a < kc; a += nwarp) {
-        const int la = rel[a];
-        const double2* row = Cm + 2 * (size_t)a * hc;
-        for (int b0 = lane; b0 < hc; b0 += 64) {
-          const int b1i = b0 + 32;
-          const bool v1 = b1i < hc;
-          const int lb0 = rel[b0], lb1 = v1 ? rel[b1i] : 0;
-          const double2 x0 = row[2 * b0], x1 = row[2 * b0 + 1];
-          double2 y0 = make_double2(0.0, 0.0), y1 = y0;
-          if (v1) { y0 = row[2 * b1i]; y1 = row[2 * b1i + 1]; }
-          const int d0 = la * nf + lb0;
-          T0[d0] = cadd(T0[d0], x0); T1[d0] = cadd(T1[d0], x1);
-          if (v1) { const int d1 = la * nf + lb1; T0[d1] = cadd(T0[d1], y0); T1[d1] = cadd(T1[d1], y1); }
-        }
-      }
-      // structure rows x pivot columns
-      for (int b = warp; b < kc; b += nwarp) {
-        const int lb = rel[b];
-        for (int a0 = kc + lane; a0 < hc; a0 += 64) {
-          const int a1 = a0 + 32;
-          const bool v1 = a1 < hc;
-          const int la0 = rel[a0] - w, la1 = v1 ? rel[a1] - w : 0;
-          const double2 x0 = Cm[2 * ((size_t)a0 * hc + b)], x1 = Cm[2 * ((size_t)a0 * hc + b) + 1];
-          double2 y0 = make_double2(0.0, 0.0), y1 = y0;
-          if (v1) { y0 = Cm[2 * ((size_t)a1 * hc + b)]; y1 = Cm[2 * ((size_t)a1 * hc + b) + 1]; }
-          const int d0 = lb * h + la0;
-          L0[d0] = cadd(L0[d0], x0); L1[d0] = cadd(L1[d0], x1);
-          if (v1) { const int d1 = lb * h + la1; L0[d1] = cadd(L0[d1], y0); L1[d1] = cadd(L1[d1], y1); }
-        }
-      }
-      for (int a = tid; a < kc; a += NT) b1[rel[a]] = cadd(b1[rel[a]], cv[a]);
-      __syncthreads();
+    const int* vptr = M.vec_ptr + P.first;
+    for (int p = tid; p < w; p += NT) {
+      double2 v = r[p];
+      for (int q = vptr[p]; q < vptr[p + 1]; ++q) v = cadd(v, Ca[M.vec_src[q]]);
+      b1[p] = v;
     }
   }
-  // ---- panel factorisation, step 1: the w x w pivot block (and the pivots' rhs) by warp 0.
-  // Rows are pre-scaled by the inverse 2x2 pivot (U' = D^-1 U), multipliers stay unscaled.
+  // ---- panel factorisation, step 1: the pivot block (w <= 16 bus blocks = at most 32 x 32 scalars) is
+  // factored entirely in the registers of warp 0: lane = scalar column, a[i] = scalar row i of that
+  // column; per 2x2 pivot the inverse is formed once, the two pivot rows are scaled in place
+  // (U' = D^-1 U), and the multipliers (kept unscaled in lanes 2p, 2p+1) are broadcast with
+  // __shfl_sync for the trailing update - no shared-memory round trips on the serial chain.
   double2* Dv0 = b1 + w;
   double2* Dv1 = Dv0 + w;
+  __syncthreads();
+  PHASE_MARK(0);   // ingest
   if (tid < 32) {
     const int lane = tid;
-    const int li = lane >> 3, lc = lane & 7;        // 4 rows x 8 columns of lanes
+    const int bc = lane >> 1, hi = lane & 1;
+    double a[32];
+#pragma unroll
+    for (int bi = 0; bi < 16; ++bi) {
+      double v0 = 0.0, v1 = 0.0;
+      if (bi < w && bc < w) {
+        const double2 t0 = T0[bi * nf + bc], t1 = T1[bi * nf + bc];
+        v0 = hi ? t0.y : t0.x;
+        v1 = hi ? t1.y : t1.x;
+      }
+      a[2 * bi] = v0;
+      a[2 * bi + 1] = v1;
+    }
     bool sing = false;
+    const unsigned full = 0xffffffffu;
+    // Compact loop (fits the instruction cache): after pivot p the register column is shifted down by two
+    // rows, so the pivot rows are always a[0], a[1] and every index below is a compile-time constant.
+    // Each step every lane stores its two pivot-row entries: scaled U' right of the pivot, the (already
+    // final) multipliers left of it.
+#pragma unroll 1
     for (int p = 0; p < w; ++p) {
-      double2 d0, d1;
-      sing |= !inv2x2(T0[p * nf + p], T1[p * nf + p], d0, d1);
-      __syncwarp();
-      for (int c = p + 1 + lane; c <= w; c += 32) {
-        if (c == w) {
-          const double2 v = b1[p];
-          b1[p] = make_double2(d0.x * v.x + d0.y * v.y, d1.x * v.x + d1.y * v.y);
-        } else {
-          const double2 u0 = T0[p * nf + c], u1 = T1[p * nf + c];
-          T0[p * nf + c] = make_double2(d0.x * u0.x + d0.y * u1.x, d0.x * u0.y + d0.y * u1.y);
-          T1[p * nf + c] = make_double2(d1.x * u0.x + d1.y * u1.x, d1.x * u0.y + d1.y * u1.y);
+      const int l0 = 2 * p, l1 = 2 * p + 1;
+      __syncwarp(full);      // lanes may still be diverged after the data-dependent ingest loops / predicated stores
+      const double p00 = __shfl_sync(full, a[0], l0), p01 = __shfl_sync(full, a[0], l1);
+      const double p10 = __shfl_sync(full, a[1], l0), p11 = __shfl_sync(full, a[1], l1);
+      // det = p00*p11 - p01*p10 with the rounding error of the product recovered by FMA (Kahan)
+      const double wq = p01 * p10;
+      const double det = fma(p00, p11, -wq) + fma(-p01, p10, wq);
+      const bool ok = isfinite(det) && det != 0.0;
+      sing |= !ok;
+      const double sc = ok ? 1.0 / det : 0.0;
+      const double d00 = p11 * sc, d01 = -p01 * sc, d10 = -p10 * sc, d11 = p00 * sc;
+      if (lane == 0) { Dv0[p] = make_double2(d00, d01); Dv1[p] = make_double2(d10, d11); }
+      const bool right = lane > l1;
+      double u0 = 0.0, u1 = 0.0;
+      if (right) {
+        u0 = d00 * a[0] + d01 * a[1];
+        u1 = d10 * a[0] + d11 * a[1];
+        a[0] = u0;
+        a[1] = u1;
+      }
+      if (bc < w) {
+        reinterpret_cast<double*>(&T0[p * nf + bc])[hi] = a[0];
+        reinterpret_cast<double*>(&T1[p * nf + bc])[hi] = a[1];
+      }
+      const int rem = 2 * (w - p);          // rows still alive in the register column (incl. the two pivot rows)
+      __syncwarp(full);
+#pragma unroll
+      for (int j = 2; j < 32; ++j) {
+        if (j < rem) {
+          const double m0 = __shfl_sync(full, a[j], l0), m1 = __shfl_sync(full, a[j], l1);
+          if (right) a[j] = fma(-m1, u1, fma(-m0, u0, a[j]));
         }
       }
-      if (lane == 0) { Dv0[p] = d0; Dv1[p] = d1; }
-      __syncwarp();
-      for (int i = p + 1 + li; i < w; i += 4) {
-        const double2 a0 = T0[i * nf + p], a1 = T1[i * nf + p];
-        for (int c = p + 1 + lc; c <= w; c += 8) {
-          if (c == w) {
-            const double2 y = b1[p];
-            double2 v = b1[i];
-            v.x = fma(-a0.x, y.x, v.x); v.x = fma(-a0.y, y.y, v.x);
-            v.y = fma(-a1.x, y.x, v.y); v.y = fma(-a1.y, y.y, v.y);
-            b1[i] = v;
-          } else {
-            bmsub(T0[i * nf + c], T1[i * nf + c], a0, a1, T0[p * nf + c], T1[p * nf + c]);
-          }
-        }
-      }
-      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 30; ++j) a[j] = a[j + 2];
+      a[30] = 0.0;
+      a[31] = 0.0;
     }
     if (sing && lane == 0) atomicOr(&A.singular[slot], 1);
+    PHASE_MARK(1);   // pivot-block chain (warp 0)
   }
   __syncthreads();
-  // ---- step 2: independent tasks, no barriers: U'12 columns (forward substitution with the
-  // multipliers of the pivot block) and L21 rows (substitution with the scaled pivot rows)
+  // ---- step 2: independent substitution tasks, no barriers: U'12 columns (and the rhs) against the
+  // multipliers of the pivot block, L21 rows against the scaled pivot rows.
   {
-    const int hpad = (h + 31) & ~31;
+    const int hpad = (h + 1 + 31) & ~31;            // column tasks: h structure columns + the rhs
     for (int t = tid; t < 2 * hpad; t += NT) {
       if (t < hpad) {
         const int b = t;
@@ -646,12 +676,25 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
             c0[p * nf] = make_double2(d0.x * x0.x + d0.y * x1.x, d0.x * x0.y + d0.y * x1.y);
             c1[p * nf] = make_double2(d1.x * x0.x + d1.y * x1.x, d1.x * x0.y + d1.y * x1.y);
           }
+        } else if (b == h) {                         // forward elimination of the pivots' rhs: y' = D^-1 (b - M y')
+          for (int p = 0; p < w; ++p) {
+            double2 v = b1[p];
+            const double2* m0 = T0 + p * nf;
+            const double2* m1 = T1 + p * nf;
+            for (int q = 0; q < p; ++q) {
+              const double2 y = b1[q];
+              v.x = fma(-m0[q].x, y.x, v.x); v.x = fma(-m0[q].y, y.y, v.x);
+              v.y = fma(-m1[q].x, y.x, v.y); v.y = fma(-m1[q].y, y.y, v.y);
+            }
+            const double2 d0 = Dv0[p], d1 = Dv1[p];
+            b1[p] = make_double2(d0.x * v.x + d0.y * v.y, d1.x * v.x + d1.y * v.y);
+          }
         }
       } else {
-        const int a = t - hpad;
-        if (a < h) {
-          double2* r0 = L0 + a;
-          double2* r1 = L1 + a;
+        const int ar = t - hpad;
+        if (ar < h) {
+          double2* r0 = L0 + ar;
+          double2* r1 = L1 + ar;
           for (int p = 1; p < w; ++p) {
             double2 x0 = r0[p * h], x1 = r1[p * h];
             for (int q = 0; q < p; ++q) bmsub(x0, x1, r0[q * h], r1[q * h], T0[q * nf + p], T1[q * nf + p]);
@@ -663,6 +706,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
     }
   }
   __syncthreads();
+  PHASE_MARK(2);   // wait for substitution tasks
   // ---- store U' panel and y'
   {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
@@ -670,6 +714,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
     double2* y = A.yv + (size_t)slot * M.m + P.first;
     for (int p = tid; p < w; p += NT) y[p] = b1[p];
   }
+  PHASE_MARK(3);   // U store issue
   if (h == 0) return;
   double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
   // ---- Schur complement straight to HBM: C = gather(children) - L * U'
@@ -708,11 +753,10 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
         }
       }
       for (int ci = 0; ci < P.nchild; ++ci) {
-        const int c = M.child_list[P.child_ptr + ci];
-        const PanelDev Cp = M.panels[c];
-        const int hc = Cp.h;
-        const int* inv = M.inv + M.inv_ptr[P.child_ptr + ci];
-        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
+        const ChildDev Cd = M.childdev[P.child_ptr + ci];
+        const int hc = Cd.hc;
+        const int* inv = M.inv + Cd.inv_off;
+        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
         const int ibA = vA ? inv[bA] : -1, ibB = vB ? inv[bB] : -1;
         // all (predicated) loads are issued before any accumulation: 16 independent 16 B loads in flight
         double2 g[4][2][2];
@@ -764,11 +808,10 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
         bmsub(acc[1][1][0], acc[1][1][1], lb0, lb1, ub0, ub1);
       }
       for (int ci = 0; ci < P.nchild; ++ci) {
-        const int c = M.child_list[P.child_ptr + ci];
-        const PanelDev Cp = M.panels[c];
-        const int hc = Cp.h;
-        const int* inv = M.inv + M.inv_ptr[P.child_ptr + ci];
-        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4);
+        const ChildDev Cd = M.childdev[P.child_ptr + ci];
+        const int hc = Cd.hc;
+        const int* inv = M.inv + Cd.inv_off;
+        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
         const int ia0 = inv[a0], ia1 = va ? inv[a0 + 1] : -1;
         const int ib0 = inv[b0], ib1 = vb ? inv[b0 + 1] : -1;
         if (ia0 >= 0 && ib0 >= 0) { const double2* sp = Cm + 2 * (ia0 * hc + ib0); acc[0][0][0] = cadd(acc[0][0][0], sp[0]); acc[0][0][1] = cadd(acc[0][0][1], sp[1]); }
@@ -784,6 +827,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
       }
     }
   }
+  PHASE_MARK(4);   // Schur (thread 0's share)
   // ---- update vector: cv[a] = gather(children) - L[a][:] y'
   double2* cvo = Co + 2 * (size_t)h * h;
   for (int a = tid; a < h; a += NT) {
@@ -794,16 +838,21 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
       v.y -= l1.x * y.x + l1.y * y.y;
     }
     for (int ci = 0; ci < P.nchild; ++ci) {
-      const int c = M.child_list[P.child_ptr + ci];
-      const PanelDev Cp = M.panels[c];
-      const int ia = M.inv[M.inv_ptr[P.child_ptr + ci] + a];
+      const ChildDev Cd = M.childdev[P.child_ptr + ci];
+      const int ia = M.inv[Cd.inv_off + a];
       if (ia >= 0) {
-        const double2* cvc = reinterpret_cast<const double2*>(Cs + Cp.c_off * 4) + 2 * (size_t)Cp.h * Cp.h;
+        const double2* cvc = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4) + 2 * (size_t)Cd.hc * Cd.hc;
         v = cadd(v, cvc[ia]);
       }
     }
     cvo[a] = v;
   }
+  PHASE_MARK(5);
+  __syncthreads();
+  PHASE_MARK(6);   // tail: slowest warp
+#ifdef SBLX_PHASE_TIMING
+  if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[NT == 32 ? 0 : NT == 64 ? 1 : NT == 128 ? 2 : NT == 256 ? 3 : 4][7], 1ull);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -592,6 +592,49 @@ static void build_from_order(int m, const std::vector<int64_t>& rowptr, const st
     }
     S.c_blocks = std::max<int64_t>(peak, 1);
   }
+  // gather-style ingest lists (need the final arena offsets)
+  {
+    S.ing_ptr.clear();
+    S.ing_src.clear();
+    S.vec_ptr.assign(m + 1, 0);
+    S.vec_src.clear();
+    std::vector<std::vector<int>> vsrc(m);
+    for (int p = 0; p < np; ++p) {
+      Panel& P = S.panels[p];
+      const int w = P.w, h = P.h, nf = w + h;
+      const int nblk = w * nf + h * w;
+      std::vector<std::vector<int>> src(nblk);
+      for (int64_t k = 0; k < P.asm_cnt; ++k) src[S.asm_dst[P.asm_ptr + k]].push_back(~S.asm_src[P.asm_ptr + k]);
+      for (int ci = 0; ci < P.nchild; ++ci) {
+        const int c = S.child_list[P.child_ptr + ci];
+        const Panel& C = S.panels[c];
+        const int hc = C.h, kc = S.kpiv[c];
+        const int* rel = &S.rel[S.rel_ptr[c]];
+        for (int a = 0; a < hc; ++a)
+          for (int b = 0; b < hc; ++b) {
+            if (a >= kc && b >= kc) continue;
+            const int la = rel[a], lb = rel[b];
+            const int dst = (la < w) ? (la * nf + lb) : (w * nf + lb * h + (la - w));
+            const int64_t off = C.c_off + (int64_t)a * hc + b;
+            if (off > 0x7fffffffLL) throw std::runtime_error("sblx symbolic: update arena too large for 32-bit ingest offsets");
+            src[dst].push_back((int)off);
+          }
+        const int64_t vbase = 2 * (C.c_off + (int64_t)hc * hc);
+        for (int a = 0; a < kc; ++a) vsrc[P.first + rel[a]].push_back((int)(vbase + a));
+      }
+      P.ing_base = (int64_t)S.ing_ptr.size();
+      for (int k = 0; k < nblk; ++k) {
+        S.ing_ptr.push_back((int)S.ing_src.size());
+        for (int v : src[k]) S.ing_src.push_back(v);
+      }
+      S.ing_ptr.push_back((int)S.ing_src.size());
+    }
+    for (int e2 = 0; e2 < m; ++e2) {
+      S.vec_ptr[e2] = (int)S.vec_src.size();
+      for (int v : vsrc[e2]) S.vec_src.push_back(v);
+    }
+    S.vec_ptr[m] = (int)S.vec_src.size();
+  }
 }
 
 void analyze(int m, const std::vector<int64_t>& rowptr, const std::vector<int>& colidx, const SymbolicOptions& opt,

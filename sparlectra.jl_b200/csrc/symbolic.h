@@ -18,7 +18,7 @@ namespace sblx {
 struct SymbolicOptions {
   int ordering = 0;            // 0 = auto (pick cheaper of ND / MD), 1 = minimum degree, 2 = nested dissection
   int smem_budget_bytes = 200 * 1024;  // panel budget per front (dynamic shared memory)
-  int max_panel_width = 32;    // cap on pivots per panel (nodes)
+  int max_panel_width = 16;    // cap on pivots per panel (the pivot block is factored in one warp's registers: 32 scalar columns)
   int relax_small = 12;        // always merge a child when the merged front has <= this many nodes
   double relax_zero_frac = 0.25;  // else merge when introduced explicit zeros <= frac * merged front area
   int nd_leaf = 48;            // nested dissection stops at subgraphs of this many nodes (ordered by MD)
@@ -36,6 +36,7 @@ struct Panel {
   int64_t struct_ptr = 0;      // into struct_nodes (h entries, ascending final elimination index)
   int64_t child_ptr = 0, nchild = 0;  // into child_list
   int64_t asm_ptr = 0, asm_cnt = 0;   // original Jacobian blocks assembled here
+  int64_t ing_base = 0;               // first entry of this panel in ing_ptr (w*(w+h) + h*w + 1 entries)
 };
 
 struct Symbolic {
@@ -55,6 +56,11 @@ struct Symbolic {
   std::vector<int> inv;
   // assembly of original entries: Jacobian block slot -> destination offset (in blocks) inside the shared-memory panel
   std::vector<int> asm_src, asm_dst;
+  // gather-style ingest: per panel block (shared-memory order: pivot rows [w][nf], then structure rows pivot-major
+  // [w][h]) the CSR list of its sources; src < 0: Jacobian slot ~src, src >= 0: block offset in the update arena
+  std::vector<int> ing_ptr, ing_src;
+  // rhs of the pivots: per elimination index the CSR list of update-vector entries (double2 index in the arena)
+  std::vector<int> vec_ptr, vec_src;
   // levels
   int nlevels = 0;
   std::vector<int> level_ptr;         // level -> range in level_panels
@@ -78,6 +84,6 @@ void analyze(int m, const std::vector<int64_t>& rowptr, const std::vector<int>& 
              Symbolic& out);
 
 // shared-memory bytes a panel needs in the factor kernel
-inline int panel_smem_bytes(int w, int h) { return ((w * (w + h) + h * w) * 4 + 6 * w + 8) * 8; }
+inline int panel_smem_bytes(int w, int h) { return ((w * (w + h) + h * w) * 4 + 6 * w + 10) * 8; }
 
 }  // namespace sblx

@@ -38,6 +38,7 @@ Base.@kwdef mutable struct SblxOptions
   base_mva::Float64 = 100.0
   mem_fraction::Float64 = 0.6
   relax_zero_frac::Float64 = 0.08
+  panel_smem_kb::Float64 = 200.0
 end
 
 # struct sblx_results: 11 pointers

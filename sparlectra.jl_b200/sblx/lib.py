@@ -24,7 +24,7 @@ class Options(C.Structure):
         ("device", C.c_int32), ("max_slots", C.c_int32), ("ordering", C.c_int32), ("relax_small", C.c_int32),
         ("tol", C.c_double), ("damp", C.c_double), ("q_hyst_pu", C.c_double), ("vm_min_pu", C.c_double),
         ("vm_max_pu", C.c_double), ("base_mva", C.c_double), ("mem_fraction", C.c_double),
-        ("relax_zero_frac", C.c_double),
+        ("relax_zero_frac", C.c_double), ("panel_smem_kb", C.c_double),
     ]
 
 
