@@ -740,10 +740,11 @@ def runpf(grid, vm, va_deg, removed=(), *, maxiter=30, tol=1e-8, damp=1.0, qlimi
         fm = max(fm, r.history[-1] if r.history else 0.0)
         Vout[idx] = r.V
         types_out[idx] = r.types
-        if not r.converged and ok:
-            ok = False
-            reason = r.reason
-    return PFResult(ok, total_it, reason if not ok else R_NONE, Vout, types_out, len(comps), nev, fm, iso)
+        if not r.converged:
+            # an island failure throws out of runpf! (rectangular_network_solver.jl:2086-2095, serial path throws at
+            # the first failing island), so _run_one_contingency reports iterations = 0 (contingency.jl:192-194,213-222)
+            return PFResult(False, 0, r.reason, Vout, types_out, len(comps), nev, fm, iso)
+    return PFResult(ok, total_it, R_NONE, Vout, types_out, len(comps), nev, fm, iso)
 
 
 def _mag_keep_angle(v, vm):

@@ -333,8 +333,12 @@ struct LaunchGroup {
 };
 
 struct HostResults {
-  std::vector<int> conv, status, iter, nsw, islands;
+  std::vector<int> conv, status, iter, nsw, islands;   // status: -1 solved on device, -2 island-wise composite, >= 0 host verdict
   std::vector<double> fm, vmin, vmax, load;
+  // island-wise solves (rectangular_network_solver.jl:1919-2243): scenario s = sub-scenarios [sub_first[s], +sub_count[s])
+  std::vector<int> sub_first, sub_count;
+  std::vector<std::vector<int>> sub_buses;   // per sub-scenario (index - B): buses of its island
+  int64_t Bint = 0;                          // scenarios on the device = B + sub-scenarios
 };
 
 }  // namespace sblx
@@ -377,7 +381,7 @@ struct sblx_handle {
   // staged batch
   int64_t B = 0;
   bool staged = false, ran = false, sweep_q = false;
-  DevBuf<int> b_queue, b_out_ptr, b_out_br, b_iso_ptr, b_iso_bus;
+  DevBuf<int> b_queue, b_out_ptr, b_out_br, b_iso_ptr, b_iso_bus, b_ref_ptr, b_ref_bus;
   DevBuf<double2> b_S, b_Vstart;
   DevBuf<double> b_ql;
   DevBuf<int> r_conv, r_status, r_iter, r_nsw;
@@ -626,7 +630,8 @@ struct TopoScratch {
 };
 
 // returns island count; fills iso (sorted). status_out: -1 = solve on device, else SBLX_ST_*
-static int analyze_scenario(const HostModel& H, const int* out, int nout, TopoScratch& ts, std::vector<int>& iso, int& status_out) {
+static int analyze_scenario(const HostModel& H, const int* out, int nout, TopoScratch& ts, std::vector<int>& iso, int& status_out,
+                            std::vector<std::vector<int>>* islands_out = nullptr) {
   const int n = H.n;
   iso = H.base_iso;
   status_out = -1;
@@ -717,6 +722,18 @@ static int analyze_scenario(const HostModel& H, const int* out, int nout, TopoSc
     for (int i = 0; i < n; ++i)
       if (!isov[i] && find(i) == i && !has_ref[i]) all_ref = false;
     status_out = all_ref ? SBLX_ST_ISLANDED_UNSUPPORTED : SBLX_ST_ISLANDED_NO_REF;
+    if (all_ref && islands_out) {
+      // islands ordered by their smallest member (ac_islands.jl:88-92); the union-find root IS the smallest member
+      std::vector<int> idx_of_root(n, -1);
+      islands_out->clear();
+      for (int i = 0; i < n; ++i) {
+        if (isov[i]) continue;
+        const int r = find(i);
+        if (idx_of_root[r] < 0) { idx_of_root[r] = (int)islands_out->size(); islands_out->emplace_back(); }
+        (*islands_out)[idx_of_root[r]].push_back(i);
+      }
+      status_out = -2;
+    }
   } else if (isov[H.slack]) {
     status_out = SBLX_ST_ISLANDED_NO_REF;
   }
@@ -743,9 +760,10 @@ static void alloc_results(sblx_handle* h, int64_t B, bool want_v, bool want_type
 
 static void set_batch(sblx_handle* h) {
   Batch& Bt = h->Bt;
-  Bt.B = (int)h->B; Bt.nq = (int)h->nq; Bt.use_sweep_q = h->sweep_q;
+  Bt.B = (int)h->hostres.Bint; Bt.nq = (int)h->nq; Bt.use_sweep_q = h->sweep_q;
   Bt.queue = h->b_queue.p; Bt.out_ptr = h->b_out_ptr.p; Bt.out_br = h->b_out_br.p;
   Bt.iso_ptr = h->b_iso_ptr.p; Bt.iso_bus = h->b_iso_bus.p;
+  Bt.ref_ptr = h->b_ref_ptr.p; Bt.ref_bus = h->b_ref_bus.p;
   Bt.Ssweep = h->b_S.p; Bt.qlsweep = h->b_ql.p; Bt.Vstart = h->b_Vstart.p;
   Bt.r_conv = h->r_conv.p; Bt.r_status = h->r_status.p; Bt.r_iter = h->r_iter.p; Bt.r_nsw = h->r_nsw.p;
   Bt.r_fm = h->r_fm.p; Bt.r_vmin = h->r_vmin.p; Bt.r_vmax = h->r_vmax.p; Bt.r_load = h->r_load.p;
@@ -764,8 +782,9 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   R.status.assign(B, -1);
   R.islands.assign(B, 1);
   std::vector<int> out_ptr(B + 1, 0), out_br;
-  std::vector<int> iso_ptr(B + 1, 0), iso_bus;
+  std::vector<int> iso_ptr(1, 0), iso_bus;
   std::vector<std::vector<int>> iso_per(B);
+  std::vector<std::vector<std::vector<int>>> isl_per(B);
   if (optr) {
     out_br.reserve(optr[B]);
     for (int64_t s = 0; s < B; ++s) {
@@ -793,7 +812,7 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
         for (int64_t s = s0; s < std::min<int64_t>(B, s0 + 64); ++s) {
           if (R.status[s] == SBLX_ST_BAD_BRANCH) { R.islands[s] = 0; continue; }
           int st;
-          R.islands[s] = analyze_scenario(H, out_br.data() + out_ptr[s], out_ptr[s + 1] - out_ptr[s], ts, iso, st);
+          R.islands[s] = analyze_scenario(H, out_br.data() + out_ptr[s], out_ptr[s + 1] - out_ptr[s], ts, iso, st, &isl_per[s]);
           R.status[s] = st;
           iso_per[s] = iso;
         }
@@ -803,13 +822,49 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
     work();
     for (auto& t : th) t.join();
   }
+  // device scenario table: the B caller scenarios, then one sub-scenario per island of every split scenario
+  // (the other islands are masked as isolated rows; an island without the slack promotes its lowest PV bus)
   std::vector<int> queue;
   queue.reserve(B);
+  std::vector<int> ref_ptr(1, 0), ref_bus;
+  R.sub_first.assign(B, 0);
+  R.sub_count.assign(B, 0);
+  R.sub_buses.clear();
   for (int64_t s = 0; s < B; ++s) {
     for (int b : iso_per[s]) iso_bus.push_back(b);
-    iso_ptr[s + 1] = (int)iso_bus.size();
-    if (R.status[s] < 0) queue.push_back((int)s);
+    iso_ptr.push_back((int)iso_bus.size());
+    ref_ptr.push_back((int)ref_bus.size());
+    if (R.status[s] == -1) queue.push_back((int)s);
   }
+  int64_t Bint = B;
+  for (int64_t s = 0; s < B; ++s) {
+    if (R.status[s] != -2) continue;
+    R.sub_first[s] = (int)Bint;
+    R.sub_count[s] = (int)isl_per[s].size();
+    for (auto& isl : isl_per[s]) {
+      std::vector<char> in(H.n, 0);
+      bool has_slack = false;
+      int promoted = -1;
+      for (int b : isl) {
+        in[b] = 1;
+        if (b == H.slack) has_slack = true;
+        if (promoted < 0 && H.type0[b] == T_PV) promoted = b;     // ascending bus order: lowest-index PV
+      }
+      for (int b = 0; b < H.n; ++b)
+        if (!in[b]) iso_bus.push_back(b);
+      iso_ptr.push_back((int)iso_bus.size());
+      if (!has_slack) ref_bus.push_back(promoted);
+      ref_ptr.push_back((int)ref_bus.size());
+      // same outage list as the parent scenario
+      const int ob = out_ptr[s], oe = out_ptr[s + 1];
+      for (int q = ob; q < oe; ++q) out_br.push_back(out_br[q]);
+      out_ptr.push_back((int)out_br.size());
+      queue.push_back((int)Bint);
+      R.sub_buses.push_back(isl);
+      ++Bint;
+    }
+  }
+  R.Bint = Bint;
   h->nq = (int64_t)queue.size();
   const double t1 = now_ms();
   h->stats = sblx_stats{};
@@ -820,8 +875,10 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   h->b_out_br.upload(out_br, h->stream);
   h->b_iso_ptr.upload(iso_ptr, h->stream);
   h->b_iso_bus.upload(iso_bus, h->stream);
+  h->b_ref_ptr.upload(ref_ptr, h->stream);
+  h->b_ref_bus.upload(ref_bus, h->stream);
   h->b_S.release(); h->b_ql.release(); h->b_Vstart.release();
-  alloc_results(h, B, want_v, want_types);
+  alloc_results(h, Bint, want_v, want_types);
   CK(cudaStreamSynchronize(h->stream));
   h->stats.h2d_bytes = (int64_t)((queue.size() + out_ptr.size() + out_br.size() + iso_ptr.size() + iso_bus.size()) * sizeof(int));
   h->stats.h2d_ms = now_ms() - t1;
@@ -969,9 +1026,9 @@ static void run_staged(sblx_handle* h) {
     CK(cudaGetLastError());
     if (st.ticks > (int64_t)(nq + 8) * (h->opt.max_iter + 2)) throw std::runtime_error("sblx: tick loop did not terminate");
   }
-  if (h->B > 0) {
-    h->r_summary.alloc((size_t)h->B * 48);
-    k_pack_summary<<<(unsigned)((h->B + 255) / 256), 256, 0, s>>>(h->Bt, h->r_summary.p);
+  if (h->hostres.Bint > 0) {
+    h->r_summary.alloc((size_t)h->hostres.Bint * 48);
+    k_pack_summary<<<(unsigned)((h->hostres.Bint + 255) / 256), 256, 0, s>>>(h->Bt, h->r_summary.p);
     st.launches++;
   }
   CK(cudaEventRecord(ev[1], s));
@@ -994,36 +1051,75 @@ static void fetch_results(sblx_handle* h, sblx_results* res) {
   if (!h->ran) throw std::invalid_argument("sblx_fetch_results: no completed run");
   const double t0 = now_ms();
   const int64_t B = h->B;
+  const HostResults& R = h->hostres;
+  const int64_t Bi = R.Bint, nsub = Bi - B;
   const int n = h->H.n;
   cudaStream_t s = h->stream;
-  std::vector<int> conv(B), status(B), iter(B), nsw(B);
-  CK(cudaMemcpyAsync(conv.data(), h->r_conv.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(status.data(), h->r_status.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(iter.data(), h->r_iter.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(nsw.data(), h->r_nsw.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-  int64_t bytes = 4 * B * sizeof(int);
-  if (res->final_mismatch) { CK(cudaMemcpyAsync(res->final_mismatch, h->r_fm.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
-  if (res->vmin_pu) { CK(cudaMemcpyAsync(res->vmin_pu, h->r_vmin.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
-  if (res->vmax_pu) { CK(cudaMemcpyAsync(res->vmax_pu, h->r_vmax.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
-  if (res->max_loading_pct) { CK(cudaMemcpyAsync(res->max_loading_pct, h->r_load.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); bytes += B * 8; }
-  if (res->V && h->r_V.p) { CK(cudaMemcpyAsync(res->V, h->r_V.p, (size_t)B * n * 16, cudaMemcpyDeviceToHost, s)); bytes += B * n * 16; }
-  if (res->bus_type_final && h->r_types.p) { CK(cudaMemcpyAsync(res->bus_type_final, h->r_types.p, (size_t)B * n, cudaMemcpyDeviceToHost, s)); bytes += B * n; }
+  std::vector<int> conv(Bi), status(Bi), iter(Bi), nsw(Bi);
+  std::vector<double> fm(Bi), vmin(Bi), vmax(Bi), load(Bi);
+  CK(cudaMemcpyAsync(conv.data(), h->r_conv.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(status.data(), h->r_status.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(iter.data(), h->r_iter.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(nsw.data(), h->r_nsw.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(fm.data(), h->r_fm.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(vmin.data(), h->r_vmin.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(vmax.data(), h->r_vmax.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(load.data(), h->r_load.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
+  int64_t bytes = Bi * (4 * sizeof(int) + 4 * sizeof(double));
+  std::vector<double2> subV;
+  std::vector<unsigned char> subT;
+  const bool wantV = res->V && h->r_V.p, wantT = res->bus_type_final && h->r_types.p;
+  if (wantV) {
+    CK(cudaMemcpyAsync(res->V, h->r_V.p, (size_t)B * n * 16, cudaMemcpyDeviceToHost, s));
+    bytes += B * n * 16;
+    if (nsub > 0) { subV.resize((size_t)nsub * n); CK(cudaMemcpyAsync(subV.data(), h->r_V.p + (size_t)B * n, (size_t)nsub * n * 16, cudaMemcpyDeviceToHost, s)); }
+  }
+  if (wantT) {
+    CK(cudaMemcpyAsync(res->bus_type_final, h->r_types.p, (size_t)B * n, cudaMemcpyDeviceToHost, s));
+    bytes += B * n;
+    if (nsub > 0) { subT.resize((size_t)nsub * n); CK(cudaMemcpyAsync(subT.data(), h->r_types.p + (size_t)B * n, (size_t)nsub * n, cudaMemcpyDeviceToHost, s)); }
+  }
   CK(cudaStreamSynchronize(s));
-  const HostResults& R = h->hostres;
   const double nan = std::nan("");
   for (int64_t k = 0; k < B; ++k) {
-    const bool host = R.status[k] >= 0;
-    if (res->converged) res->converged[k] = host ? 0 : (uint8_t)conv[k];
-    if (res->status) res->status[k] = host ? R.status[k] : status[k];
-    if (res->iterations) res->iterations[k] = host ? 0 : iter[k];
-    if (res->n_switch_events) res->n_switch_events[k] = host ? 0 : nsw[k];
-    if (res->island_count) res->island_count[k] = R.islands[k];
-    if (host) {
-      if (res->final_mismatch) res->final_mismatch[k] = nan;
-      if (res->vmin_pu) res->vmin_pu[k] = nan;
-      if (res->vmax_pu) res->vmax_pu[k] = nan;
-      if (res->max_loading_pct) res->max_loading_pct[k] = nan;
+    int c = 0, st = 0, it = 0, sw = 0;
+    double f = nan, lo = nan, hi = nan, ld = nan;
+    if (R.status[k] == -1) {
+      c = conv[k]; st = status[k]; it = iter[k]; sw = nsw[k]; f = fm[k]; lo = vmin[k]; hi = vmax[k]; ld = load[k];
+    } else if (R.status[k] == -2) {
+      // island-wise composite: iterations summed, converged only if every island converged; the first failing
+      // island (island order) aborts the case with iterations = 0 (the reference throws out of runpf!)
+      c = 1; f = 0.0;
+      bool any_ld = false;
+      for (int q = 0; q < R.sub_count[k]; ++q) {
+        const int64_t u = R.sub_first[k] + q;
+        if (!conv[u]) { c = 0; st = status[u]; it = 0; break; }
+        it += iter[u]; sw += nsw[u];
+        f = std::max(f, fm[u]);
+        lo = std::isnan(lo) ? vmin[u] : std::min(lo, vmin[u]);
+        hi = std::isnan(hi) ? vmax[u] : std::max(hi, vmax[u]);
+        if (!std::isnan(load[u])) { ld = any_ld ? std::max(ld, load[u]) : load[u]; any_ld = true; }
+      }
+      if (!c) { f = nan; lo = nan; hi = nan; ld = nan; sw = 0; }
+      for (int q = 0; q < R.sub_count[k]; ++q) {
+        const int64_t u = R.sub_first[k] + q - B;
+        for (int b : R.sub_buses[u]) {
+          if (wantV) reinterpret_cast<double2*>(res->V)[(size_t)k * n + b] = subV[(size_t)u * n + b];
+          if (wantT) res->bus_type_final[(size_t)k * n + b] = subT[(size_t)u * n + b];
+        }
+      }
+    } else {
+      st = R.status[k];
     }
+    if (res->converged) res->converged[k] = (uint8_t)c;
+    if (res->status) res->status[k] = st;
+    if (res->iterations) res->iterations[k] = it;
+    if (res->n_switch_events) res->n_switch_events[k] = sw;
+    if (res->island_count) res->island_count[k] = R.islands[k];
+    if (res->final_mismatch) res->final_mismatch[k] = f;
+    if (res->vmin_pu) res->vmin_pu[k] = lo;
+    if (res->vmax_pu) res->vmax_pu[k] = hi;
+    if (res->max_loading_pct) res->max_loading_pct[k] = ld;
   }
   h->stats.d2h_ms = now_ms() - t0;
   h->stats.d2h_bytes = bytes;

@@ -77,6 +77,7 @@ struct Lists {
 struct Batch {
   int B, nq, use_sweep_q;
   const int* queue; const int* out_ptr; const int* out_br; const int* iso_ptr; const int* iso_bus;
+  const int* ref_ptr; const int* ref_bus;     // per scenario: PV buses promoted to island reference (ac_islands.jl:228-234)
   const double2* Ssweep; const double* qlsweep; const double2* Vstart;
   // results
   int* r_conv; int* r_status; int* r_iter; int* r_nsw; double* r_fm; double* r_vmin; double* r_vmax; double* r_load;
@@ -228,6 +229,19 @@ __global__ void k_init_iso(DevModel M, Slots A, Lists L, Batch Bt) {
     A.S[k] = make_double2(0.0, 0.0);
     A.V[k] = make_double2(1.0, 0.0);
   }
+  if (Bt.ref_ptr) {
+    // promoted island reference: held like a slack at |V| = Vset with the start angle
+    // (rectangular_network_solver.jl:523 on the island sub-net, ac_islands.jl:400-413)
+    for (int q = Bt.ref_ptr[scen]; q < Bt.ref_ptr[scen + 1]; ++q) {
+      const int bus = Bt.ref_bus[q];
+      const size_t k = (size_t)bus * M.W + slot;
+      A.type[k] = T_SLACK;
+      const double2 v = A.V[k];
+      const double vm = sqrt(v.x * v.x + v.y * v.y);
+      const double vs = M.vset[bus];
+      A.V[k] = vm > 0.0 ? make_double2(v.x * (vs / vm), v.y * (vs / vm)) : make_double2(vs, 0.0);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -275,7 +289,8 @@ __global__ void __launch_bounds__(256) k_mismatch(DevModel M, Slots A, Lists L) 
     A.I[k] = I;
     if (bus != M.slack) {
       const double2 Sc = cmul(Vi, cconj(I));
-      const double2 F = residual_rows(A.type[k], Vi, Sc, A.S[k], M.vset[bus]);
+      const int ty = A.type[k];
+      const double2 F = (ty == T_SLACK) ? make_double2(0.0, 0.0) : residual_rows(ty, Vi, Sc, A.S[k], M.vset[bus]);
       const int e = M.elim_of_node[M.node_of_bus[bus]];
       A.rhs[(size_t)slot * M.m + e] = make_double2(-F.x, -F.y);
       unsigned long long b0 = abs_bits(F.x), b1 = abs_bits(F.y);
@@ -443,8 +458,8 @@ __global__ void __launch_bounds__(256) k_jacobian(DevModel M, Slots A, Lists L) 
   const size_t ki = (size_t)i * W + slot;
   double b00 = 0, b01 = 0, b10 = 0, b11 = 0;
   const bool isoi = A.iso[ki] != 0, isoj = A.iso[(size_t)j * W + slot] != 0;
-  if (isoi || isoj) {
-    if (i == j) { b00 = 1.0; b11 = 1.0; }              // neutral identity row/col: delta = 0
+  if (isoi || isoj || A.type[ki] == T_SLACK) {
+    if (i == j) { b00 = 1.0; b11 = 1.0; }              // neutral identity row (isolated bus / promoted island reference): delta = 0
   } else {
     double2 y = M.y_val[M.jb_ypos[ent]];
     const int no = A.out_cnt[slot];
@@ -998,6 +1013,7 @@ __global__ void __launch_bounds__(256) k_fin_branch(DevModel M, Slots A, Lists L
   for (int o = 0; o < no; ++o)
     if (A.out_br[slot * MAXOUT + o] == br) return;
   const int f = M.br_from[br], t = M.br_to[br];
+  if (A.iso[(size_t)f * M.W + slot] || A.iso[(size_t)t * M.W + slot]) return;
   const double2 Vf = A.V[(size_t)f * M.W + slot], Vt = A.V[(size_t)t * M.W + slot];
   const double2 If = cadd(cmul(M.y11[br], Vf), cmul(M.y12[br], Vt));
   const double2 It = cadd(cmul(M.y22[br], Vt), cmul(M.y21[br], Vf));

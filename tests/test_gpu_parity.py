@@ -78,9 +78,7 @@ def _compare_batch(g, cases, raw, oracle_results, label, allow_unsupported=True)
     nflip = 0
     for i, (c, o) in enumerate(zip(cases, oracle_results)):
         st = int(raw["status"][i])
-        if st == 9:                      # islanded with own reference: flagged, not solved
-            assert allow_unsupported and o.island_count >= 2, (label, i, c)
-            continue
+        assert st != 9, (label, i, c)      # island-wise solves are supported
         assert bool(raw["converged"][i]) == o.converged, (label, i, c, st, o.reason)
         assert int(raw["island_count"][i]) == o.island_count, (label, i, c)
         if o.reason == O.R_ISLANDED_NO_REF:
@@ -199,6 +197,32 @@ def test_islanding_and_divergence_are_reported_not_thrown():
     assert not res[1].converged and "unknown branch" in res[1].error
     o = O.run_contingencies(g, [[2]])
     assert not o[0].converged
+
+
+def test_island_with_pv_is_promoted_and_solved_island_wise():
+    """test/test_contingency.jl:118-139: cutting B-C leaves {C, D} with a PV generator at C; the reference promotes it to
+    the island's angle reference and solves both islands (island_count == 2, iterations summed)."""
+    g = G.island_chain(with_pv=True)
+    res, raw = api.runContingenciesBatched(g, [api.ContingencyCase("B_ACL_2_3")], return_raw=True)
+    o = O.run_contingencies(g, [[1]])[0]
+    assert o.converged and o.island_count == 2
+    assert res[0].converged and res[0].island_count == 2 and res[0].iterations == o.iterations
+    assert np.max(np.abs(raw["V"][0] - o.V)) <= VTOL
+    assert np.array_equal(raw["bus_type_final"][0], o.types.astype(np.uint8))
+    assert abs(res[0].min_vm_pu - o.min_vm_pu) <= 1e-9 and abs(res[0].max_vm_pu - o.max_vm_pu) <= 1e-9
+
+
+def test_ladder_split_into_two_referenced_islands():
+    """warm-up 118 ladder: taking both rails out between buses 15/16 and 74/75 splits it into two islands, the right one
+    without the slack: its lowest PV bus (21) becomes the reference (ac_islands.jl:228-234)."""
+    g = G.warmup_case118()
+    ka = [k for k in range(g.nbranch) if (g.br_from[k], g.br_to[k]) == (14, 15)][0]
+    kb = [k for k in range(g.nbranch) if (g.br_from[k], g.br_to[k]) == (73, 74)][0]
+    cases = [[ka, kb], [ka], [kb], [3, 70]]
+    raw, oracle, _ = _run_both(g, cases)
+    assert oracle[0].island_count == 2 and oracle[0].converged
+    assert raw["bus_type_final"][0][20] == 3          # promoted reference reported as Slack, like the island sub-net
+    _compare_batch(g, cases, raw, oracle, "ladder-split")
 
 
 def test_twin_circuits_get_their_own_case():
