@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--relax-small", type=int, default=0)
     ap.add_argument("--relax-frac", type=float, default=0.0)
     ap.add_argument("--panel-kb", type=float, default=0.0)
+    ap.add_argument("--factor-mode", type=int, default=-1)
     return ap.parse_args()
 
 
@@ -176,6 +177,8 @@ def main():
         extra["relax_zero_frac"] = args.relax_frac
     if args.panel_kb > 0:
         extra["panel_smem_kb"] = args.panel_kb
+    if args.factor_mode >= 0:
+        extra["factor_mode"] = args.factor_mode
     eng = api.Engine(a0, device=local_rank, max_slots=args.max_slots, ordering=args.ordering, **extra)
     t_create = time.perf_counter() - t0
     Vb, conv, itb, resb, stb = eng.solve_one(None)

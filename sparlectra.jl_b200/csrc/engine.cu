@@ -330,6 +330,7 @@ static double host_selftest(const HostModel& H, uint64_t seed) {
 // ------------------------------------------------------------------------------------------
 struct LaunchGroup {
   int off, cnt, nt, smem;     // range in d_level_panels, threads, dynamic smem bytes
+  int subst_chunks = 0, schur_tiles = 0, wmax = 0;   // split path: grid.z of k_subst / k_schur, widest panel
 };
 
 struct HostResults {
@@ -365,12 +366,15 @@ struct sblx_handle {
   DevBuf<long long> d_rel_ptr, d_inv_ptr;
   std::vector<std::vector<LaunchGroup>> front_groups;   // per level
   std::vector<std::vector<LaunchGroup>> solve_groups;
+  std::vector<LaunchGroup> level_all;                   // per level: all its panels (k_pivot)
+  long long l_blocks = 1;
   DevModel M{};
   // slots
   int W = 0;
   size_t bytes_per_slot = 0;
   DevBuf<double2> s_V, s_I, s_S, s_rhs, s_yv, s_xv;
-  DevBuf<double> s_qload, s_Jv, s_U, s_C, s_fm;
+  DevBuf<double> s_qload, s_Jv, s_U, s_C, s_fm, s_Lw;
+  DevBuf<double2> s_Dw;
   DevBuf<unsigned char> s_type, s_iso, s_evcnt, s_evact;
   DevBuf<short> s_evlast;
   DevBuf<int> s_scen, s_iter, s_state, s_changed, s_nev, s_singular, s_numerical, s_reason, s_viol, s_maxsw, s_rated, s_out_cnt, s_out_br;
@@ -438,10 +442,21 @@ static void upload_model(sblx_handle* h) {
   h->d_y22.upload(H.y22, s);
   h->d_rating.upload(H.rating, s);
   h->d_br_status.upload(H.br_status, s);
+  std::vector<int> l_off(S.panels.size(), 0);
+  h->l_blocks = 1;
+  for (int l = 0; l < S.nlevels; ++l) {
+    long long off = 0;
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      const Panel& P = S.panels[S.level_panels[q]];
+      l_off[S.level_panels[q]] = (int)off;
+      off += (long long)P.h * P.w;
+    }
+    h->l_blocks = std::max(h->l_blocks, off);
+  }
   std::vector<PanelDev> pd(S.panels.size());
   for (size_t i = 0; i < pd.size(); ++i) {
     const Panel& P = S.panels[i];
-    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.ing_base, 0, (long long)P.u_off, (long long)P.c_off};
+    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.ing_base, l_off[i], (long long)P.u_off, (long long)P.c_off};
   }
   h->d_panels.upload(pd, s);
   h->d_struct.upload(S.struct_nodes, s);
@@ -467,7 +482,9 @@ static void upload_model(sblx_handle* h) {
   h->d_rel_ptr.upload(rp, s);
   h->d_inv_ptr.upload(ip, s);
   // launch groups: per level, panels sorted by size class
-  auto front_class = [](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 72 * 1024 ? 2 : bytes <= 110 * 1024 ? 3 : 4; };
+  // size class by panel bytes; the two small classes factor the pivot block with an 8-pivot register column
+  auto front_class_b = [](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 72 * 1024 ? 2 : bytes <= 110 * 1024 ? 3 : 4; };
+  auto front_class_p = [&](const Panel& P) { int c = front_class_b(panel_smem_bytes(P.w, P.h)); return (P.w > 8 && c < 2) ? 2 : c; };
   static const int front_nt[5] = {32, 64, 128, 256, 512};
   std::vector<int> lp;
   h->front_groups.assign(S.nlevels, {});
@@ -475,24 +492,34 @@ static void upload_model(sblx_handle* h) {
   for (int l = 0; l < S.nlevels; ++l) {
     std::vector<int> ids(S.level_panels.begin() + S.level_ptr[l], S.level_panels.begin() + S.level_ptr[l + 1]);
     std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
-      return front_class(panel_smem_bytes(S.panels[a].w, S.panels[a].h)) < front_class(panel_smem_bytes(S.panels[b].w, S.panels[b].h));
+      return front_class_p(S.panels[a]) < front_class_p(S.panels[b]);
     });
     size_t i = 0;
     while (i < ids.size()) {
-      int c = front_class(panel_smem_bytes(S.panels[ids[i]].w, S.panels[ids[i]].h));
+      int c = front_class_p(S.panels[ids[i]]);
       size_t j = i;
       int smem = 0, hs = 0;
-      while (j < ids.size() && front_class(panel_smem_bytes(S.panels[ids[j]].w, S.panels[ids[j]].h)) == c) {
+      while (j < ids.size() && front_class_p(S.panels[ids[j]]) == c) {
         smem = std::max(smem, panel_smem_bytes(S.panels[ids[j]].w, S.panels[ids[j]].h));
         hs = std::max(hs, S.panels[ids[j]].h + S.panels[ids[j]].w);
         ++j;
       }
       LaunchGroup g{(int)lp.size() + (int)i, (int)(j - i), front_nt[c], smem};
+      for (size_t q = i; q < j; ++q) {
+        const Panel& P = S.panels[ids[q]];
+        const int hpad = (P.h + 31) & ~31;
+        g.subst_chunks = std::max(g.subst_chunks, (2 * hpad + 127) / 128);
+        g.schur_tiles = std::max(g.schur_tiles, ((P.h + 31) / 32) * ((P.h + 63) / 64));
+        g.wmax = std::max(g.wmax, P.w);
+      }
       h->front_groups[l].push_back(g);
       LaunchGroup gs{g.off, g.cnt, hs <= 32 ? 32 : hs <= 96 ? 64 : 128, hs * 16 + 64};
       h->solve_groups[l].push_back(gs);
       i = j;
     }
+    LaunchGroup ga{(int)lp.size(), (int)ids.size(), 128, 0};
+    if ((int)h->level_all.size() <= l) h->level_all.resize(l + 1);
+    h->level_all[l] = ga;
     lp.insert(lp.end(), ids.begin(), ids.end());
   }
   h->d_level_panels.upload(lp, s);
@@ -503,6 +530,8 @@ static void upload_model(sblx_handle* h) {
   CK(cudaFuncSetAttribute(k_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   CK(cudaFuncSetAttribute(k_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   CK(cudaFuncSetAttribute(k_front<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CK(cudaFuncSetAttribute(k_subst, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
+  CK(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(k_backsolve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(k_backsolve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(k_backsolve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -522,7 +551,7 @@ static void upload_model(sblx_handle* h) {
   M.asm_src = h->d_asm_src.p; M.asm_dst = h->d_asm_dst.p;
   M.ing_ptr = h->d_ing_ptr.p; M.ing_src = h->d_ing_src.p; M.vec_ptr = h->d_vec_ptr.p; M.vec_src = h->d_vec_src.p;
   M.childdev = h->d_childdev.p;
-  M.u_blocks = S.u_blocks; M.c_blocks = S.c_blocks + 2;
+  M.u_blocks = S.u_blocks; M.c_blocks = S.c_blocks + 2; M.l_blocks = h->l_blocks;
   const sblx_options& o = h->opt;
   M.tol = o.tol; M.damp = o.damp; M.hyst = o.q_hyst_pu; M.vm_min = o.vm_min_pu; M.vm_max = o.vm_max_pu; M.base_mva = o.base_mva;
   M.max_iter = o.max_iter; M.qlim_enabled = o.qlimits_enabled; M.qlim_start = o.qlimit_start_iter; M.cooldown = o.cooldown_iters;
@@ -578,6 +607,10 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   h->s_Jv.alloc((size_t)H.jb_col.size() * 4 * W);
   h->s_U.alloc((size_t)h->M.u_blocks * 4 * W);
   h->s_C.alloc((size_t)h->M.c_blocks * 4 * W);
+  if (h->opt.factor_mode == 1) {
+    h->s_Lw.alloc((size_t)h->M.l_blocks * 4 * W);
+    h->s_Dw.alloc((size_t)2 * m * W);
+  }
   h->s_scen.alloc(W); h->s_iter.alloc(W); h->s_state.alloc(W); h->s_changed.alloc(W); h->s_nev.alloc(W);
   h->s_singular.alloc(W); h->s_numerical.alloc(W); h->s_reason.alloc(W); h->s_viol.alloc(W); h->s_maxsw.alloc(W);
   h->s_rated.alloc(W); h->s_out_cnt.alloc(W); h->s_out_br.alloc((size_t)W * MAXOUT); h->s_fm.alloc(W);
@@ -589,6 +622,7 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   A.V = h->s_V.p; A.I = h->s_I.p; A.S = h->s_S.p; A.qload_s = nullptr;
   A.type = h->s_type.p; A.iso = h->s_iso.p; A.evcnt = h->s_evcnt.p; A.evact = h->s_evact.p; A.evlast = h->s_evlast.p;
   A.rhs = h->s_rhs.p; A.Jv = h->s_Jv.p; A.U = h->s_U.p; A.C = h->s_C.p; A.yv = h->s_yv.p; A.xv = h->s_xv.p;
+  A.Lw = h->s_Lw.p; A.Dw = h->s_Dw.p;
   A.scen = h->s_scen.p; A.iter = h->s_iter.p; A.state = h->s_state.p; A.changed = h->s_changed.p; A.nev = h->s_nev.p;
   A.singular = h->s_singular.p; A.numerical = h->s_numerical.p; A.reason = h->s_reason.p;
   A.mis_bits = h->s_mis.p; A.mis2_bits = h->s_mis2.p; A.fm = h->s_fm.p;
@@ -898,6 +932,46 @@ static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
   k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
 }
 
+// numeric factorisation of the step set: level by level
+static void launch_factor(sblx_handle* h, int nstep) {
+  sblx_stats& st = h->stats;
+  cudaStream_t s = h->stream;
+  for (size_t l = 0; l < h->front_groups.size(); ++l) {
+    if (h->opt.factor_mode != 1) {
+      for (const LaunchGroup& g : h->front_groups[l]) {
+        switch (g.nt) {
+          case 32: launch_front<32>(h, g, nstep); break;
+          case 64: launch_front<64>(h, g, nstep); break;
+          case 128: launch_front<128>(h, g, nstep); break;
+          case 256: launch_front<256>(h, g, nstep); break;
+          default: launch_front<512>(h, g, nstep); break;
+        }
+        st.launches++;
+        st.factor_launches++;
+      }
+    } else {
+      const LaunchGroup& ga = h->level_all[l];
+      k_pivot<<<dim3(ga.cnt, (nstep + 3) / 4), dim3(32, 4), 0, s>>>(h->M, h->A, h->L, h->d_level_panels.p + ga.off);
+      st.launches++;
+      st.factor_launches++;
+      for (const LaunchGroup& g : h->front_groups[l]) {
+        if (g.subst_chunks == 0) continue;
+        const int sm_sub = (2 * g.wmax * g.wmax + 2 * g.wmax) * 16;
+        k_subst<<<dim3(g.cnt, nstep, g.subst_chunks), 128, sm_sub, s>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+        st.launches++;
+        st.factor_launches++;
+      }
+      for (const LaunchGroup& g : h->front_groups[l]) {
+        if (g.schur_tiles == 0) continue;
+        const int sm_sch = g.wmax * (2 * 32 + 2 * 64) * 16;
+        k_schur<<<dim3(g.cnt, nstep, g.schur_tiles), 128, sm_sch, s>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+        st.launches++;
+        st.factor_launches++;
+      }
+    }
+  }
+}
+
 static void run_staged(sblx_handle* h) {
   if (!h->staged) throw std::invalid_argument("sblx_run_staged: nothing staged");
   ensure_cuda(h);
@@ -974,20 +1048,7 @@ static void run_staged(sblx_handle* h) {
       st.launches++;
     }
     CK(cudaEventRecord(ev[4], s));
-    if (nstep > 0) {
-      for (size_t l = 0; l < h->front_groups.size(); ++l)
-        for (const LaunchGroup& g : h->front_groups[l]) {
-          switch (g.nt) {
-            case 32: launch_front<32>(h, g, nstep); break;
-            case 64: launch_front<64>(h, g, nstep); break;
-            case 128: launch_front<128>(h, g, nstep); break;
-            case 256: launch_front<256>(h, g, nstep); break;
-            default: launch_front<512>(h, g, nstep); break;
-          }
-          st.launches++;
-          st.factor_launches++;
-        }
-    }
+    if (nstep > 0) launch_factor(h, nstep);
     CK(cudaEventRecord(ev[5], s));
     if (nstep > 0) {
       for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
@@ -1159,7 +1220,8 @@ void sblx_default_options(sblx_options* o) {
   o->device = -1;
   o->max_slots = 0;
   o->ordering = 0;
-  o->relax_small = 28;
+  o->relax_small = 18;
+  o->factor_mode = 0;
   o->tol = 1e-8;
   o->damp = 1.0;
   o->q_hyst_pu = 0.0;
@@ -1482,16 +1544,7 @@ int sblx_debug_newton_step(sblx_handle* h, int64_t nout, const int32_t* outage_b
   CK(cudaMemcpyAsync(h->l_counts.p, one, sizeof one, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->l_step.p, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
   k_jacobian<<<dim3((nnzB + 7) / 8, 1), dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
-  for (size_t l = 0; l < h->front_groups.size(); ++l)
-    for (const LaunchGroup& g : h->front_groups[l]) {
-      switch (g.nt) {
-        case 32: launch_front<32>(h, g, 1); break;
-        case 64: launch_front<64>(h, g, 1); break;
-        case 128: launch_front<128>(h, g, 1); break;
-        case 256: launch_front<256>(h, g, 1); break;
-        default: launch_front<512>(h, g, 1); break;
-      }
-    }
+  launch_factor(h, 1);
   for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
     for (const LaunchGroup& g : h->solve_groups[l]) {
       switch (g.nt) {

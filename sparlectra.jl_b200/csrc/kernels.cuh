@@ -29,7 +29,7 @@ constexpr int T_ISO = 0, T_PQ = 1, T_PV = 2, T_SLACK = 3;
 
 struct PanelDev {
   int first, w, h, nchild;
-  int struct_ptr, child_ptr, ing_base, pad0;
+  int struct_ptr, child_ptr, ing_base, l_off;   // l_off: level-local offset (blocks) of this panel's L21 in the Lw workspace
   long long u_off, c_off;
 };
 // per (parent, child) record used by the Schur gather
@@ -50,7 +50,7 @@ struct DevModel {
   const PanelDev* panels; const int* struct_nodes; const int* child_list; const int* rel; const long long* rel_ptr;
   const int* kpiv; const int* inv; const long long* inv_ptr; const int* asm_src; const int* asm_dst;
   const int* ing_ptr; const int* ing_src; const int* vec_ptr; const int* vec_src; const ChildDev* childdev;
-  long long u_blocks, c_blocks;
+  long long u_blocks, c_blocks, l_blocks;
   double tol, damp, hyst, vm_min, vm_max, base_mva;
   int max_iter, qlim_enabled, qlim_start, cooldown, guard, freeze, allow_reenable;
 };
@@ -61,6 +61,7 @@ struct Slots {
   unsigned char* type; unsigned char* iso; unsigned char* evcnt; unsigned char* evact; short* evlast;
   // [W][...]
   double2* rhs; double* Jv; double* U; double* C; double2* yv; double2* xv;
+  double* Lw; double2* Dw;   // split path: L21 workspace [W][l_blocks*4], inverse pivot blocks [W][2*m]
   // [W]
   int* scen; int* iter; int* state; int* changed; int* nev; int* singular; int* numerical; int* reason;
   unsigned long long* mis_bits; unsigned long long* mis2_bits; double* fm;
@@ -538,7 +539,7 @@ __device__ __forceinline__ void bmsub(double2& t0, double2& t1, double2 a0, doub
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 ? 10 : NT == 32 ? 16 : 1)) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
   extern __shared__ double2 sm2[];
   const int panel = panel_ids[blockIdx.x];
   if ((int)blockIdx.y >= L.counts[2]) return;
@@ -560,35 +561,48 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
   double* Cs = A.C + (size_t)slot * M.c_blocks * 4;
   // ---- gather-style ingest: every panel block sums its sources (its Jacobian block, then the matching
   // blocks of the children's update matrices, in child order) and is written to shared memory once.
-  {
-    const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
-    const double2* Ca = reinterpret_cast<const double2*>(Cs);
-    const int* iptr = M.ing_ptr + P.ing_base;
-    const int* isrc = M.ing_src;
-    const int nblk = nT + nL;
-    for (int k0 = tid; k0 < nblk; k0 += 2 * NT) {
-      const int k1 = k0 + NT;
-      const bool v1 = k1 < nblk;
-      const int s0 = iptr[k0], e0 = iptr[k0 + 1];
-      const int s1 = v1 ? iptr[k1] : 0, e1 = v1 ? iptr[k1 + 1] : 0;
-      double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
-      int q0 = s0, q1 = s1;
-      while (q0 < e0 || q1 < e1) {           // the two blocks' source loads are interleaved (independent)
-        double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1v = a0;
-        if (q0 < e0) {
-          const int sidx = isrc[q0++];
-          const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
-          a0 = ptr[0]; a1 = ptr[1];
-        }
-        if (q1 < e1) {
-          const int sidx = isrc[q1++];
-          const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
-          b0 = ptr[0]; b1v = ptr[1];
-        }
-        x0 = cadd(x0, a0); x1 = cadd(x1, a1); y0 = cadd(y0, b0); y1 = cadd(y1, b1v);
+  // Phase A (all threads): the w x w pivot block and the pivots' rhs.  Phase B: the rest of the panel - in a
+  // multi-warp CTA it is done by warps 1.. WHILE warp 0 factors the pivot block in registers.
+  const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
+  const double2* Ca = reinterpret_cast<const double2*>(Cs);
+  const int* iptr = M.ing_ptr + P.ing_base;
+  const int* isrc = M.ing_src;
+  auto ingest_block = [&](int k) {
+    double2 x0 = make_double2(0.0, 0.0), x1 = x0;
+    const int s0 = iptr[k], e0 = iptr[k + 1];
+    for (int q = s0; q < e0; ++q) {
+      const int sidx = isrc[q];
+      const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+      x0 = cadd(x0, ptr[0]); x1 = cadd(x1, ptr[1]);
+    }
+    if (k < nT) { T0[k] = x0; T1[k] = x1; } else { L0[k - nT] = x0; L1[k - nT] = x1; }
+  };
+  auto ingest_pair = [&](int k0, int k1, bool v1) {     // two blocks with interleaved (independent) source loads
+    const int s0 = iptr[k0], e0 = iptr[k0 + 1];
+    const int s1 = v1 ? iptr[k1] : 0, e1 = v1 ? iptr[k1 + 1] : 0;
+    double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
+    int q0 = s0, q1 = s1;
+    while (q0 < e0 || q1 < e1) {
+      double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1v = a0;
+      if (q0 < e0) {
+        const int sidx = isrc[q0++];
+        const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+        a0 = ptr[0]; a1 = ptr[1];
       }
-      if (k0 < nT) { T0[k0] = x0; T1[k0] = x1; } else { L0[k0 - nT] = x0; L1[k0 - nT] = x1; }
-      if (v1) { if (k1 < nT) { T0[k1] = y0; T1[k1] = y1; } else { L0[k1 - nT] = y0; L1[k1 - nT] = y1; } }
+      if (q1 < e1) {
+        const int sidx = isrc[q1++];
+        const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+        b0 = ptr[0]; b1v = ptr[1];
+      }
+      x0 = cadd(x0, a0); x1 = cadd(x1, a1); y0 = cadd(y0, b0); y1 = cadd(y1, b1v);
+    }
+    if (k0 < nT) { T0[k0] = x0; T1[k0] = x1; } else { L0[k0 - nT] = x0; L1[k0 - nT] = x1; }
+    if (v1) { if (k1 < nT) { T0[k1] = y0; T1[k1] = y1; } else { L0[k1 - nT] = y0; L1[k1 - nT] = y1; } }
+  };
+  {
+    for (int t = tid; t < w * w; t += NT) {            // pivot block: rows i < w, columns j < w
+      const int i = t / w, j = t - i * w;
+      ingest_block(i * nf + j);
     }
     const double2* r = A.rhs + (size_t)slot * M.m + P.first;
     const int* vptr = M.vec_ptr + P.first;
@@ -598,6 +612,19 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
       b1[p] = v;
     }
   }
+  // the rest of the panel: T columns j >= w of every pivot row, then all structure-row blocks
+  auto ingest_rest = [&](int t0, int tstep) {
+    const int nTr = w * h;                               // T blocks right of the pivot block
+    const int nrest = nTr + nL;
+    for (int t = t0; t < nrest; t += 2 * tstep) {
+      const int u = t + tstep;
+      const bool v1 = u < nrest;
+      int k0, k1 = 0;
+      if (t < nTr) { const int i = t / h, j = t - i * h; k0 = i * nf + w + j; } else k0 = nT + (t - nTr);
+      if (v1) { if (u < nTr) { const int i = u / h, j = u - i * h; k1 = i * nf + w + j; } else k1 = nT + (u - nTr); }
+      ingest_pair(k0, k1, v1);
+    }
+  };
   // ---- panel factorisation, step 1: the pivot block (w <= 16 bus blocks = at most 32 x 32 scalars) is
   // factored entirely in the registers of warp 0: lane = scalar column, a[i] = scalar row i of that
   // column; per 2x2 pivot the inverse is formed once, the two pivot rows are scaled in place
@@ -606,13 +633,15 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
   double2* Dv0 = b1 + w;
   double2* Dv1 = Dv0 + w;
   __syncthreads();
-  PHASE_MARK(0);   // ingest
+  PHASE_MARK(0);   // ingest of the pivot block
+  if (NT > 32 && tid >= 32) ingest_rest(tid - 32, NT - 32);
   if (tid < 32) {
     const int lane = tid;
     const int bc = lane >> 1, hi = lane & 1;
-    double a[32];
+    constexpr int WR = (NT <= 64) ? 8 : 16;      // small classes only hold fronts with w <= 8 (host class rule)
+    double a[2 * WR];
 #pragma unroll
-    for (int bi = 0; bi < 16; ++bi) {
+    for (int bi = 0; bi < WR; ++bi) {
       double v0 = 0.0, v1 = 0.0;
       if (bi < w && bc < w) {
         const double2 t0 = T0[bi * nf + bc], t1 = T1[bi * nf + bc];
@@ -657,19 +686,20 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
       const int rem = 2 * (w - p);          // rows still alive in the register column (incl. the two pivot rows)
       __syncwarp(full);
 #pragma unroll
-      for (int j = 2; j < 32; ++j) {
+      for (int j = 2; j < 2 * WR; ++j) {
         if (j < rem) {
           const double m0 = __shfl_sync(full, a[j], l0), m1 = __shfl_sync(full, a[j], l1);
           if (right) a[j] = fma(-m1, u1, fma(-m0, u0, a[j]));
         }
       }
 #pragma unroll
-      for (int j = 0; j < 30; ++j) a[j] = a[j + 2];
-      a[30] = 0.0;
-      a[31] = 0.0;
+      for (int j = 0; j < 2 * WR - 2; ++j) a[j] = a[j + 2];
+      a[2 * WR - 2] = 0.0;
+      a[2 * WR - 1] = 0.0;
     }
     if (sing && lane == 0) atomicOr(&A.singular[slot], 1);
     PHASE_MARK(1);   // pivot-block chain (warp 0)
+    if (NT == 32) ingest_rest(tid, NT);
   }
   __syncthreads();
   // ---- step 2: independent substitution tasks, no barriers: U'12 columns (and the rhs) against the
@@ -863,11 +893,333 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : 1)) k_fro
     cvo[a] = v;
   }
   PHASE_MARK(5);
+#ifdef SBLX_PHASE_TIMING
   __syncthreads();
   PHASE_MARK(6);   // tail: slowest warp
+#endif
 #ifdef SBLX_PHASE_TIMING
   if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[NT == 32 ? 0 : NT == 64 ? 1 : NT == 128 ? 2 : NT == 256 ? 3 : 4][7], 1ull);
 #endif
+}
+
+// ==========================================================================================
+// Split factorisation path: three streaming kernels per level instead of one fused CTA per front.
+//   k_pivot : one WARP per (front, scenario): gathers the w x w pivot block + rhs straight into
+//             registers, factors it (same register/shuffle chain as above), writes the factored
+//             block (multipliers + scaled rows), the inverse pivots and y' to HBM.
+//   k_subst : one THREAD per U'12 column / L21 row: gathers its column into registers (all loads in
+//             flight at once), substitutes against the factored pivot block (shared memory, 8 KB),
+//             writes U'12 into the U panel and L21 into a level-local workspace.
+//   k_schur : one CTA per 32 x 64 tile of F22: loads the L / U' strips of the tile, register-tile
+//             FMA loop, gathers the children's contributions, writes the update matrix once.
+// Only small per-CTA shared memory -> many CTAs per SM; every kernel is a coalesced stream.
+// ==========================================================================================
+__device__ __forceinline__ const double2* ing_source(int sidx, const double2* Jv, const double2* Ca) {
+  return sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+}
+
+// grid (panels, ceil(nStep/4)), block (32, 4)
+__global__ void __launch_bounds__(128) k_pivot(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+  const int lane = threadIdx.x;
+  const int si = blockIdx.y * 4 + threadIdx.y;
+  if (si >= L.counts[2]) return;
+  const int slot = L.step[si];
+  const PanelDev P = M.panels[panel_ids[blockIdx.x]];
+  const int w = P.w, nf = P.w + P.h;
+  const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
+  const double2* Ca = reinterpret_cast<const double2*>(A.C + (size_t)slot * M.c_blocks * 4);
+  const int* iptr = M.ing_ptr + P.ing_base;
+  const int* isrc = M.ing_src;
+  const int bc = lane >> 1, hi = lane & 1;
+  const unsigned full = 0xffffffffu;
+  constexpr int WR = 16;
+  double a[2 * WR];
+#pragma unroll
+  for (int i = 0; i < 2 * WR; ++i) a[i] = 0.0;
+  for (int r = 0; r < 64; ++r) {             // source rounds: all pivot-block loads of one round are independent
+    bool any = false;
+#pragma unroll
+    for (int bi = 0; bi < WR; ++bi) {
+      if (bi < w && bc < w) {
+        const int k = bi * nf + bc;
+        const int s0 = iptr[k] + r;
+        if (s0 < iptr[k + 1]) {
+          const double2* ptr = ing_source(isrc[s0], Jv, Ca);
+          const double2 r0 = ptr[0], r1 = ptr[1];
+          a[2 * bi] += hi ? r0.y : r0.x;
+          a[2 * bi + 1] += hi ? r1.y : r1.x;
+          any = true;
+        }
+      }
+    }
+    if (!__any_sync(full, any)) break;
+  }
+  // rhs: lane i holds scalar row i of the pivots' right-hand side
+  double rb = 0.0;
+  if (lane < 2 * w) {
+    const int p = lane >> 1;
+    double2 v = A.rhs[(size_t)slot * M.m + P.first + p];
+    const int* vptr = M.vec_ptr + P.first;
+    for (int q = vptr[p]; q < vptr[p + 1]; ++q) v = cadd(v, Ca[M.vec_src[q]]);
+    rb = (lane & 1) ? v.y : v.x;
+  }
+  double2* Up = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
+  double2* Dw = A.Dw + ((size_t)slot * M.m + P.first) * 2;
+  bool sing = false;
+#pragma unroll 1
+  for (int p = 0; p < w; ++p) {
+    const int l0 = 2 * p, l1 = 2 * p + 1;
+    __syncwarp(full);
+    const double p00 = __shfl_sync(full, a[0], l0), p01 = __shfl_sync(full, a[0], l1);
+    const double p10 = __shfl_sync(full, a[1], l0), p11 = __shfl_sync(full, a[1], l1);
+    const double wq = p01 * p10;
+    const double det = fma(p00, p11, -wq) + fma(-p01, p10, wq);
+    const bool ok = isfinite(det) && det != 0.0;
+    sing |= !ok;
+    const double sc = ok ? 1.0 / det : 0.0;
+    const double d00 = p11 * sc, d01 = -p01 * sc, d10 = -p10 * sc, d11 = p00 * sc;
+    if (lane == 0) { Dw[2 * p] = make_double2(d00, d01); Dw[2 * p + 1] = make_double2(d10, d11); }
+    const double yr0 = __shfl_sync(full, rb, l0), yr1 = __shfl_sync(full, rb, l1);
+    const double y0 = d00 * yr0 + d01 * yr1, y1 = d10 * yr0 + d11 * yr1;
+    if (lane == l0) rb = y0;
+    if (lane == l1) rb = y1;
+    const bool right = lane > l1;
+    double u0 = 0.0, u1 = 0.0;
+    if (right) {
+      u0 = d00 * a[0] + d01 * a[1];
+      u1 = d10 * a[0] + d11 * a[1];
+      a[0] = u0;
+      a[1] = u1;
+    }
+    if (bc < w) {
+      reinterpret_cast<double*>(&Up[2 * (p * nf + bc)])[hi] = a[0];
+      reinterpret_cast<double*>(&Up[2 * (p * nf + bc) + 1])[hi] = a[1];
+    }
+    const int rem = 2 * (w - p);
+    __syncwarp(full);
+#pragma unroll
+    for (int j = 2; j < 2 * WR; ++j) {
+      if (j < rem) {
+        const double m0 = __shfl_sync(full, a[j], l0), m1 = __shfl_sync(full, a[j], l1);
+        if (right) a[j] = fma(-m1, u1, fma(-m0, u0, a[j]));
+        if (lane == l0 + j) rb = fma(-m1, y1, fma(-m0, y0, rb));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * WR - 2; ++j) a[j] = a[j + 2];
+    a[2 * WR - 2] = 0.0;
+    a[2 * WR - 1] = 0.0;
+  }
+  if (lane < 2 * w) reinterpret_cast<double*>(&A.yv[(size_t)slot * M.m + P.first + (lane >> 1)])[lane & 1] = rb;
+  if (sing && lane == 0) atomicOr(&A.singular[slot], 1);
+}
+
+// grid (panels, nStep, chunks of 128 tasks), block 128
+__global__ void __launch_bounds__(128, 3) k_subst(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+  extern __shared__ double2 sm2[];
+  const PanelDev P = M.panels[panel_ids[blockIdx.x]];
+  const int w = P.w, h = P.h, nf = w + h;
+  const int hpad = (h + 31) & ~31;
+  if ((int)blockIdx.z * 128 >= 2 * hpad) return;
+  if ((int)blockIdx.y >= L.counts[2]) return;
+  const int slot = L.step[blockIdx.y];
+  const int tid = threadIdx.x;
+  double2* M0 = sm2;            // factored pivot block, block-row planes [w][w]
+  double2* M1 = M0 + w * w;
+  double2* D0 = M1 + w * w;     // inverse pivots [w]
+  double2* D1 = D0 + w;
+  double2* Up = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
+  {
+    const double2* Dw = A.Dw + ((size_t)slot * M.m + P.first) * 2;
+    for (int i = tid; i < w * w; i += 128) {
+      const int r = i / w, c = i - r * w;
+      M0[i] = Up[2 * (r * nf + c)];
+      M1[i] = Up[2 * (r * nf + c) + 1];
+    }
+    for (int p = tid; p < w; p += 128) { D0[p] = Dw[2 * p]; D1[p] = Dw[2 * p + 1]; }
+  }
+  const int t = blockIdx.z * 128 + tid;
+  const bool is_col = t < hpad;
+  const int idx = is_col ? t : t - hpad;
+  const bool live = idx < h;
+  const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
+  const double2* Ca = reinterpret_cast<const double2*>(A.C + (size_t)slot * M.c_blocks * 4);
+  const int* iptr = M.ing_ptr + P.ing_base;
+  const int* isrc = M.ing_src;
+  constexpr int WR = 16;
+  double2 x0[WR], x1[WR];
+#pragma unroll
+  for (int p = 0; p < WR; ++p) { x0[p] = make_double2(0.0, 0.0); x1[p] = x0[p]; }
+  if (live) {
+    // panel block of entry p of this task: column task -> (p, w + idx) in the pivot rows, row task -> L[p][idx]
+    const int kbase = is_col ? (w + idx) : (w * nf + idx);
+    const int kstep = is_col ? nf : h;
+    for (int r = 0; r < 64; ++r) {
+      bool any = false;
+#pragma unroll
+      for (int p = 0; p < WR; ++p) {
+        if (p < w) {
+          const int k = kbase + p * kstep;
+          const int s0 = iptr[k] + r;
+          if (s0 < iptr[k + 1]) {
+            const double2* ptr = ing_source(isrc[s0], Jv, Ca);
+            x0[p] = cadd(x0[p], ptr[0]);
+            x1[p] = cadd(x1[p], ptr[1]);
+            any = true;
+          }
+        }
+      }
+      if (!any) break;
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  if (is_col) {
+    double2* out = Up + 2 * (w + idx);
+#pragma unroll 1
+    for (int q = 0; q < w; ++q) {
+      const double2 d0 = D0[q], d1 = D1[q];
+      const double2 u0 = make_double2(d0.x * x0[0].x + d0.y * x1[0].x, d0.x * x0[0].y + d0.y * x1[0].y);
+      const double2 u1 = make_double2(d1.x * x0[0].x + d1.y * x1[0].x, d1.x * x0[0].y + d1.y * x1[0].y);
+      out[2 * (q * nf)] = u0;
+      out[2 * (q * nf) + 1] = u1;
+#pragma unroll
+      for (int j = 1; j < WR; ++j) {
+        if (q + j < w) bmsub(x0[j], x1[j], M0[(q + j) * w + q], M1[(q + j) * w + q], u0, u1);
+        x0[j - 1] = x0[j];
+        x1[j - 1] = x1[j];
+      }
+    }
+  } else {
+    double2* out = reinterpret_cast<double2*>(A.Lw + ((size_t)slot * M.l_blocks + P.l_off) * 4) + 2 * idx;
+#pragma unroll 1
+    for (int q = 0; q < w; ++q) {
+      const double2 l0 = x0[0], l1 = x1[0];
+      out[2 * (q * h)] = l0;
+      out[2 * (q * h) + 1] = l1;
+#pragma unroll
+      for (int j = 1; j < WR; ++j) {
+        if (q + j < w) bmsub(x0[j], x1[j], l0, l1, M0[q * w + q + j], M1[q * w + q + j]);
+        x0[j - 1] = x0[j];
+        x1[j - 1] = x1[j];
+      }
+    }
+  }
+}
+
+// grid (panels, nStep, tiles), block 128: tile = 32 structure rows x 64 structure columns of F22
+__global__ void __launch_bounds__(128, 4) k_schur(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+  extern __shared__ double2 sm2[];
+  const PanelDev P = M.panels[panel_ids[blockIdx.x]];
+  const int w = P.w, h = P.h, nf = w + h;
+  if (h == 0) return;
+  const int ntc = (h + 63) >> 6, ntr = (h + 31) >> 5;
+  if ((int)blockIdx.z >= ntr * ntc) return;
+  if ((int)blockIdx.y >= L.counts[2]) return;
+  const int slot = L.step[blockIdx.y];
+  const int tr = blockIdx.z / ntc, tc = blockIdx.z - tr * ntc;
+  const int a_base = tr * 32, b_base = tc * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2* L0 = sm2;              // [w][32]
+  double2* L1 = L0 + w * 32;
+  double2* U0 = L1 + w * 32;      // [w][64]
+  double2* U1 = U0 + w * 64;
+  const double2* Lg = reinterpret_cast<const double2*>(A.Lw + ((size_t)slot * M.l_blocks + P.l_off) * 4);
+  const double2* Ug = reinterpret_cast<const double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
+  for (int i = tid; i < w * 32; i += 128) {
+    const int p = i >> 5, r = i & 31;
+    const int a = min(a_base + r, h - 1);
+    L0[i] = Lg[2 * (p * h + a)];
+    L1[i] = Lg[2 * (p * h + a) + 1];
+  }
+  for (int i = tid; i < w * 64; i += 128) {
+    const int p = i >> 6, c = i & 63;
+    const int b = min(b_base + c, h - 1);
+    U0[i] = Ug[2 * (p * nf + w + b)];
+    U1[i] = Ug[2 * (p * nf + w + b) + 1];
+  }
+  __syncthreads();
+  double* Cs = A.C + (size_t)slot * M.c_blocks * 4;
+  double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
+  const int bA = b_base + lane, bB = bA + 32;
+  const bool vA = bA < h, vB = bB < h;
+  for (int rg = warp; rg < 8; rg += 4) {
+    const int a0 = a_base + rg * 4;
+    if (a0 >= h) break;
+    double2 acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { acc[i][j][0] = make_double2(0.0, 0.0); acc[i][j][1] = make_double2(0.0, 0.0); }
+    const double2* lp0 = L0 + rg * 4;
+    const double2* lp1 = L1 + rg * 4;
+    const double2* up0 = U0 + lane;
+    const double2* up1 = U1 + lane;
+#pragma unroll 2
+    for (int p = 0; p < w; ++p) {
+      const double2 ua0 = up0[p * 64], ua1 = up1[p * 64];
+      const double2 ub0 = up0[p * 64 + 32], ub1 = up1[p * 64 + 32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 l0 = lp0[p * 32 + i], l1 = lp1[p * 32 + i];
+        bmsub(acc[i][0][0], acc[i][0][1], l0, l1, ua0, ua1);
+        bmsub(acc[i][1][0], acc[i][1][1], l0, l1, ub0, ub1);
+      }
+    }
+    for (int ci = 0; ci < P.nchild; ++ci) {
+      const ChildDev Cd = M.childdev[P.child_ptr + ci];
+      const int hc = Cd.hc;
+      const int* inv = M.inv + Cd.inv_off;
+      const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
+      const int ibA = vA ? inv[bA] : -1, ibB = vB ? inv[bB] : -1;
+      double2 g[4][2][2];
+      int ia[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ia[i] = (a0 + i < h) ? inv[a0 + i] : -1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool okA = ia[i] >= 0 && ibA >= 0, okB = ia[i] >= 0 && ibB >= 0;
+        const double2* spA = Cm + 2 * ((size_t)(okA ? ia[i] : 0) * hc + (okA ? ibA : 0));
+        const double2* spB = Cm + 2 * ((size_t)(okB ? ia[i] : 0) * hc + (okB ? ibB : 0));
+        const double2 z = make_double2(0.0, 0.0);
+        g[i][0][0] = okA ? spA[0] : z; g[i][0][1] = okA ? spA[1] : z;
+        g[i][1][0] = okB ? spB[0] : z; g[i][1][1] = okB ? spB[1] : z;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0][0] = cadd(acc[i][0][0], g[i][0][0]); acc[i][0][1] = cadd(acc[i][0][1], g[i][0][1]);
+        acc[i][1][0] = cadd(acc[i][1][0], g[i][1][0]); acc[i][1][1] = cadd(acc[i][1][1], g[i][1][1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (a0 + i >= h) break;
+      if (vA) { Co[2 * ((size_t)(a0 + i) * h + bA)] = acc[i][0][0]; Co[2 * ((size_t)(a0 + i) * h + bA) + 1] = acc[i][0][1]; }
+      if (vB) { Co[2 * ((size_t)(a0 + i) * h + bB)] = acc[i][1][0]; Co[2 * ((size_t)(a0 + i) * h + bB) + 1] = acc[i][1][1]; }
+    }
+  }
+  // update vector of the tile's rows (first tile column only): cv[a] = gather(children) - L[a][:] y'
+  if (tc == 0 && tid < 32) {
+    const int a = a_base + tid;
+    if (a < h) {
+      const double2* y = A.yv + (size_t)slot * M.m + P.first;
+      double2 v = make_double2(0.0, 0.0);
+      for (int p = 0; p < w; ++p) {
+        const double2 l0 = L0[p * 32 + tid], l1 = L1[p * 32 + tid], yy = y[p];
+        v.x = fma(-l0.x, yy.x, v.x); v.x = fma(-l0.y, yy.y, v.x);
+        v.y = fma(-l1.x, yy.x, v.y); v.y = fma(-l1.y, yy.y, v.y);
+      }
+      for (int ci = 0; ci < P.nchild; ++ci) {
+        const ChildDev Cd = M.childdev[P.child_ptr + ci];
+        const int ia = M.inv[Cd.inv_off + a];
+        if (ia >= 0) {
+          const double2* cvc = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4) + 2 * (size_t)Cd.hc * Cd.hc;
+          v = cadd(v, cvc[ia]);
+        }
+      }
+      Co[2 * (size_t)h * h + a] = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

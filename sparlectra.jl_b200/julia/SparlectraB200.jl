@@ -29,7 +29,9 @@ Base.@kwdef mutable struct SblxOptions
   device::Int32 = -1
   max_slots::Int32 = 0
   ordering::Int32 = 0
-  relax_small::Int32 = 28
+  relax_small::Int32 = 18
+  factor_mode::Int32 = 0
+  reserved1::Int32 = 0
   tol::Float64 = 1e-8
   damp::Float64 = 1.0
   q_hyst_pu::Float64 = 0.0

@@ -22,6 +22,7 @@ class Options(C.Structure):
         ("qlimits_enabled", C.c_int32), ("qlimit_start_iter", C.c_int32), ("cooldown_iters", C.c_int32),
         ("guard_max_switches", C.c_int32), ("freeze_after_repeated_switching", C.c_int32),
         ("device", C.c_int32), ("max_slots", C.c_int32), ("ordering", C.c_int32), ("relax_small", C.c_int32),
+        ("factor_mode", C.c_int32), ("reserved1", C.c_int32),
         ("tol", C.c_double), ("damp", C.c_double), ("q_hyst_pu", C.c_double), ("vm_min_pu", C.c_double),
         ("vm_max_pu", C.c_double), ("base_mva", C.c_double), ("mem_fraction", C.c_double),
         ("relax_zero_frac", C.c_double), ("panel_smem_kb", C.c_double),

@@ -235,6 +235,14 @@ def test_twin_circuits_get_their_own_case():
     assert res[0].min_vm_pu != res[1].min_vm_pu
 
 
+def test_split_kernel_path_matches_oracle():
+    """The experimental split factorisation (k_pivot / k_subst / k_schur, factor_mode=1) must give the same answers."""
+    g = G.tiled_grid(rows=12, cols=12, augment=True, pv_every=4, pv_q_mvar=24.0, rating_mva=60.0)
+    cases = O.generate_n1_branches(g)[:80]
+    raw, oracle, _ = _run_both(g, cases, factor_mode=1)
+    _compare_batch(g, cases, raw, oracle, "split")
+
+
 def test_injection_sweep_parity():
     g = G.tiled_grid(rows=10, cols=10, augment=True, pv_every=3, pv_q_mvar=20.0)
     vm, va, flat, base = O.solve_base(g)
