@@ -309,3 +309,50 @@ def test_medium_grid_properties_54x54():
         assert np.max(np.abs(F)) <= 1e-8
         qg = Sc.imag + ql
         assert np.all((qg[sw] >= qmax[sw] - 1e-6) | (qg[sw] <= qmin[sw] + 1e-6))
+
+
+def test_full_size_10k_grid_parity_and_properties():
+    """BASELINE config 4/5 grid (100x100 tiled, 10 000 buses, 29 601 branches): a spread of N-1 and N-2 outages.
+    Three scenarios are compared against the oracle in full (iterations, active set, voltages <= 1e-8); every
+    sampled scenario must satisfy the canonical mismatch evaluated by the oracle's function at the returned V."""
+    g = G.tiled_grid(rows=100, cols=100, augment=True, rating_mva=100.0)
+    a0 = M.build_arrays(g)
+    eng = api.Engine(a0)
+    Vb, conv, itb, resb, stb = eng.solve_one(None)
+    ob = O.runpf(g, g.vm0, g.va0_deg, ())
+    assert conv and ob.converged and itb == ob.iters and np.max(np.abs(Vb - ob.V)) <= VTOL
+    vm, va = np.abs(Vb), np.degrees(np.angle(Vb))
+    a = M.build_arrays(g, vm=vm, va_deg=va)
+    eng.set_v0(a.v0)
+    rng = np.random.default_rng(3)
+    n1 = [[int(k)] for k in rng.choice(g.nbranch, size=200, replace=False)]
+    n2 = [sorted(int(x) for x in rng.choice(g.nbranch, size=2, replace=False)) for _ in range(56)]
+    cases = n1 + n2
+    raw = eng.solve_outages(cases)
+    info = eng.info()
+    eng.close()
+    assert info["nnz_lu_scalar"] > 2_000_000 and raw["converged"].mean() > 0.98
+    for i in (0, 101, 230):
+        o = O.runpf(g, vm, va, cases[i])
+        assert bool(raw["converged"][i]) == o.converged and int(raw["iterations"][i]) == o.iters
+        assert np.max(np.abs(raw["V"][i] - o.V)) <= VTOL
+        assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8))
+    S = O.complex_svec(g)
+    vset = O.voltage_setpoints(g, vm)
+    for i in range(0, len(cases), 16):
+        if not raw["converged"][i]:
+            continue
+        Y = O.create_ybus(g, cases[i])
+        t = raw["bus_type_final"][i].astype(np.int64)
+        Sc = O.calc_injections(Y, raw["V"][i])
+        Sx = S.copy()
+        sw = (a.bus_type == M.BUS_PV) & (t == M.BUS_PQ)
+        Sx[sw] = Sx[sw].real + 1j * Sc[sw].imag
+        t2 = np.where(t == 0, 1, t)
+        F = O.mismatch_rectangular_fast(Y, raw["V"][i], Sx, t2, vset, a.slack)
+        iso = (t == 0)
+        if iso.any():       # isolated buses carry neutral rows
+            ns = np.array([b for b in range(g.n) if b != a.slack])
+            keep = np.repeat(~iso[ns], 2)
+            F = F[keep]
+        assert np.max(np.abs(F)) <= 1e-8
