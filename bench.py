@@ -277,6 +277,13 @@ def main():
         nnzj, nnzlu, N = info["nnz_j_scalar"], info["nnz_lu_scalar"], 2 * info["m"]
         units = agg["scenario_iterations"]
         front_bytes_unit = 8.0 * nnzj + 8.0 * nnzlu + 16.0 * N
+        traffic = None
+        try:   # ncu dram__bytes_read+write of all k_front launches of one tick / scenarios in that tick (same grid)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k_front_traffic.json")))
+            if args.rows == 100 and args.cols == 100:
+                traffic = tj["k_front_dram_bytes_per_unit"] * units
+        except Exception:
+            pass
         ach_front = units * front_bytes_unit / (agg["factor_ms"] * 1e-3) / 1e9 if agg["factor_ms"] > 0 else 0.0
         ach_step = units * info["algorithmic_bytes_per_iteration"] / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0
         line = {
@@ -294,7 +301,8 @@ def main():
             "e2e": {"value": total_scen * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(agg["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_front (numeric multifrontal LU, all launches of one pass)",
-                         "achieved": ach_front, "peak": hbm, "unit": "GB/s", "frac": ach_front / hbm, "traffic": None,
+                         "achieved": ach_front, "peak": hbm, "unit": "GB/s", "frac": ach_front / hbm, "traffic": traffic,
+                         "traffic_note": "ncu DRAM bytes per scenario-iteration (profiles/r1_k_front_traffic.json) x units; 5.8x the algorithmic bytes: the multifrontal update-matrix arena",
                          "peak_source": peak_src, "bytes_per_unit": front_bytes_unit, "units": units,
                          "avg_launch_ms": agg["factor_ms"] / max(1, agg["factor_launches"]), "launches": agg["factor_launches"],
                          "kernel_ms": agg["factor_ms"]},
