@@ -113,6 +113,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def cpu_sample_size(g, ncores):
+    """Bounded CPU sample: about 15 s of work (the oracle port needs ~0.12 ms per bus per scenario on one core)."""
+    per_scen_s = max(1e-3, 1.2e-4 * g.n)
+    return int(min(max(ncores, 8, ncores * round(15.0 / per_scen_s)), 4096))
+
+
 def cpu_reference_rate(g, vm, va, cases, nsample, nproc):
     """The reference's CPU path (oracle port) on a bounded sample, scenarios in contiguous chunks
     over `nproc` worker processes (contingency.jl:304-312 fans chunks out over threads)."""
@@ -121,10 +127,11 @@ def cpu_reference_rate(g, vm, va, cases, nsample, nproc):
     chunks = [sample[i::nproc] for i in range(nproc)]
     chunks = [c for c in chunks if c]
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
     with ctx.Pool(len(chunks), initializer=_cpu_init, initargs=(g, vm, va)) as pool:
-        res = pool.map(_cpu_chunk, chunks)
-    dt = time.perf_counter() - t0
+        pool.map(_cpu_chunk, [[] for _ in chunks])      # workers forked and imports done before the clock starts
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_chunk, chunks, chunksize=1)
+        dt = time.perf_counter() - t0
     its = sum(r[1] for r in res)
     return len(sample) / dt, dt, its
 
@@ -261,7 +268,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1
-        ns = args.cpu_sample or max(ncores, 8)
+        ns = min(len(mine), args.cpu_sample or cpu_sample_size(g, ncores))
         rate, dt, its = cpu_reference_rate(g, vm, va, mine, ns, ncores)
         cpu = {"value": rate, "unit": UNIT, "cores": ncores, "kind": "port",
                "sample": f"first {ns} N-1 scenarios of the same workload, oracle port (numpy + SuperLU, one process per core), "
@@ -281,7 +288,7 @@ def main():
         try:   # ncu dram__bytes_read+write of all k_front launches of one tick / scenarios in that tick (same grid)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k_front_traffic.json")))
             if args.rows == 100 and args.cols == 100:
-                traffic = tj["k_front_dram_bytes_per_unit"] * units
+                traffic = tj["k_front_dram_bytes_per_unit"] * units / max(1, agg["factor_launches"])
         except Exception:
             pass
         ach_front = units * front_bytes_unit / (agg["factor_ms"] * 1e-3) / 1e9 if agg["factor_ms"] > 0 else 0.0
@@ -302,7 +309,8 @@ def main():
             "gpu_launches": int(agg["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_front (numeric multifrontal LU, all launches of one pass)",
                          "achieved": ach_front, "peak": hbm, "unit": "GB/s", "frac": ach_front / hbm, "traffic": traffic,
-                         "traffic_note": "ncu DRAM bytes per scenario-iteration (profiles/r1_k_front_traffic.json) x units; 5.8x the algorithmic bytes: the multifrontal update-matrix arena",
+                         "algorithmic_bytes_per_launch": units * front_bytes_unit / max(1, agg["factor_launches"]),
+                         "traffic_note": "bytes per launch: ncu dram read+write per scenario-iteration (profiles/r1_k_front_traffic.json) x units / launches; 5.8x the algorithmic bytes = the multifrontal update-matrix arena",
                          "peak_source": peak_src, "bytes_per_unit": front_bytes_unit, "units": units,
                          "avg_launch_ms": agg["factor_ms"] / max(1, agg["factor_launches"]), "launches": agg["factor_launches"],
                          "kernel_ms": agg["factor_ms"]},
@@ -329,7 +337,7 @@ def reference_arm(args, rank, world):
     g, cases, per_rank, wname = workload(args, 1)
     vm, va, flat, base = O.solve_base(g)
     ncores = os.cpu_count() or 1
-    ns = args.cpu_sample or max(ncores, 8)
+    ns = min(len(cases), args.cpu_sample or cpu_sample_size(g, ncores))
     rates = []
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_rate(g, vm, va, cases, ns, ncores)
