@@ -166,6 +166,7 @@ static void build_nodes_and_symbolic(HostModel& H, const sblx_options& o) {
   so.relax_zero_frac = o.relax_zero_frac;
   if (o.relax_small > 0) so.relax_small = o.relax_small;
   if (o.panel_smem_kb >= 4.0 && o.panel_smem_kb <= 200.0) so.smem_budget_bytes = (int)(o.panel_smem_kb * 1024);
+  if (const char* e = getenv("SBLX_ND_LEAF")) so.nd_leaf = std::max(4, atoi(e));   // tuning probe
   analyze(H.m, H.jb_rowptr, H.jb_col, so, H.sym);
   if (H.sym.max_w > 16) throw std::runtime_error("sblx: panel wider than 16 pivots");
 }
@@ -923,12 +924,12 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
 
 template <int NT>
 static void launch_front(sblx_handle* h, const LaunchGroup& g, int nstep) {
-  dim3 grid(g.cnt, nstep);
+  dim3 grid = SBLX_SWAP ? dim3(nstep, g.cnt) : dim3(g.cnt, nstep);
   k_front<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
 }
 template <int NT>
 static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
-  dim3 grid(g.cnt, nstep);
+  dim3 grid = SBLX_SWAP ? dim3(nstep, g.cnt) : dim3(g.cnt, nstep);
   k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
 }
 

@@ -538,12 +538,22 @@ __device__ __forceinline__ void bmsub(double2& t0, double2& t1, double2 a0, doub
   t1.y = fma(-a1.x, u0.y, t1.y); t1.y = fma(-a1.y, u1.y, t1.y);
 }
 
+#ifndef SBLX_OCC32
+#define SBLX_OCC32 16
+#endif
+#ifndef SBLX_OCC64
+#define SBLX_OCC64 10
+#endif
+#ifndef SBLX_SWAP
+#define SBLX_SWAP 1   // scenario = fastest grid dimension: co-resident CTAs run the SAME front of different scenarios (shared index lists hit L1, one code path)
+#endif
 template <int NT>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 ? 10 : NT == 32 ? 16 : 1)) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 ? SBLX_OCC64 : NT == 32 ? SBLX_OCC32 : 1)) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
   extern __shared__ double2 sm2[];
-  const int panel = panel_ids[blockIdx.x];
-  if ((int)blockIdx.y >= L.counts[2]) return;
-  const int slot = L.step[blockIdx.y];
+  const int bpanel = SBLX_SWAP ? blockIdx.y : blockIdx.x, bscen = SBLX_SWAP ? blockIdx.x : blockIdx.y;
+  const int panel = panel_ids[bpanel];
+  if (bscen >= L.counts[2]) return;
+  const int slot = L.step[bscen];
   const PanelDev P = M.panels[panel];
   const int w = P.w, h = P.h, nf = w + h;
   const int tid = threadIdx.x;
@@ -1228,9 +1238,10 @@ __global__ void __launch_bounds__(128, 4) k_schur(DevModel M, Slots A, Lists L, 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
   extern __shared__ double2 sm2[];
-  const int panel = panel_ids[blockIdx.x];
-  if ((int)blockIdx.y >= L.counts[2]) return;
-  const int slot = L.step[blockIdx.y];
+  const int bpanel = SBLX_SWAP ? blockIdx.y : blockIdx.x, bscen = SBLX_SWAP ? blockIdx.x : blockIdx.y;
+  const int panel = panel_ids[bpanel];
+  if (bscen >= L.counts[2]) return;
+  const int slot = L.step[bscen];
   const PanelDev P = M.panels[panel];
   const int w = P.w, h = P.h, nf = w + h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

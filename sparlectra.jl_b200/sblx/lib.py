@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsblx.so")
+LIB_PATH = os.environ.get("SBLX_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsblx.so")
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)

@@ -167,3 +167,38 @@ def test_product_path_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".jl")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "sparlectra_oracle" not in txt and "import oracle" not in txt, f
+
+
+# ---- MATPOWER .m reader (rules of src/MatpowerIO.jl:268-514) ----
+def test_matpower_reader_case14_equals_embedded_tables():
+    from sblx import matpower as MP
+    here = os.path.dirname(os.path.abspath(__file__))
+    c = MP.read_case_m(os.path.join(here, "golden", "case14.m"))
+    assert c["name"] == "case14" and c["baseMVA"] == 100.0
+    assert c["bus"].shape == (14, 13) and c["gen"].shape == (5, 21) and c["branch"].shape == (20, 13)
+    g1, g0 = MP.grid_from_case(os.path.join(here, "golden", "case14.m")), G.case14()
+    a1, a0 = M.build_arrays(g1), M.build_arrays(g0)
+    for f in ("y11", "y12", "y21", "y22", "s_spec", "vset", "v0", "qmin", "qmax", "qload", "bus_type", "br_rating"):
+        np.testing.assert_array_equal(getattr(a1, f), getattr(a0, f), err_msg=f)
+    assert (a1.Y != a0.Y).nnz == 0
+
+
+def test_matpower_reader_text_rules():
+    from sblx import matpower as MP
+    txt = ("function mpc = tiny\n% header ; with [ brackets ]; inside a comment\nmpc.baseMVA = 50.5;\n"
+           "mpc.bus = [ 3 1 10 5 0 0 1 1.0 0 110 1 1.1 0.9   % unsorted, newline-separated rows (RTS-GMLC style)\n"
+           "  1 3 0 0 0 0 1 1.02 0 110 1 1.1 0.9\n\n  2 2 0 0 0 0 1 1.01 0 110 1 1.1 0.9 99 98 ];\n"
+           "mpc.gen = [1 50 0 100 -100 1.02 100 1 150 0; 2 25 0 80 -80 1.01 100 1 100 0;];\n"
+           "mpc.branch = [1 2 0.02 0.08 0.02 999 999 999 0 0 1;\r\n 2 3 0.02 0.08 0.02 0 0 0 0 0 1; 1 3 0.03 0.1 0 0 0 0 1.0 5 1 -360 360 7];\n")
+    c = MP.read_case_m(txt)
+    assert c["name"] == "tiny" and c["baseMVA"] == 50.5
+    assert c["bus"][:, 0].tolist() == [1.0, 2.0, 3.0]          # legacy_sort_bus
+    assert c["bus"].shape == (3, 13)                            # extra tokens truncated
+    assert c["gen"].shape == (2, 21) and np.all(c["gen"][:, 10:] == 0.0)   # short rows zero-padded
+    assert c["branch"].shape == (3, 13) and c["branch"][2, 8] == 1.0 and c["branch"][0, 8] == 0.0   # raw TAP kept
+    g = MP.grid_from_case(txt)
+    assert g.n == 3 and g.nbranch == 3 and g.baseMVA == 50.5
+    with pytest.raises(ValueError, match="baseMVA"):
+        MP.read_case_m("mpc.bus = [1 2 3];\n")
+    with pytest.raises(ValueError, match="mpc.gen"):
+        MP.read_case_m("mpc.baseMVA = 100;\nmpc.bus = [1 3 0 0 0 0 1 1 0 1 1 1 1];\n")
