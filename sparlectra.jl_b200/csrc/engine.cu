@@ -332,6 +332,7 @@ static double host_selftest(const HostModel& H, uint64_t seed) {
 struct LaunchGroup {
   int off, cnt, nt, smem;     // range in d_level_panels, threads, dynamic smem bytes
   int subst_chunks = 0, schur_tiles = 0, wmax = 0;   // split path: grid.z of k_subst / k_schur, widest panel
+  int lanes = 0;              // k_front: lanes per scenario (< nt: several scenarios share one warp)
 };
 
 struct HostResults {
@@ -484,9 +485,25 @@ static void upload_model(sblx_handle* h) {
   h->d_inv_ptr.upload(ip, s);
   // launch groups: per level, panels sorted by size class
   // size class by panel bytes; the two small classes factor the pivot block with an 8-pivot register column
-  auto front_class_b = [](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 72 * 1024 ? 2 : bytes <= 110 * 1024 ? 3 : 4; };
-  auto front_class_p = [&](const Panel& P) { int c = front_class_b(panel_smem_bytes(P.w, P.h)); return (P.w > 8 && c < 2) ? 2 : c; };
-  static const int front_nt[5] = {32, 64, 128, 256, 512};
+  // Classes 0/1 are the lane-group kernels (8 / 16 lanes per scenario: pivot blocks of <= 4 / <= 8 buses, 4 / 2
+  // scenarios per warp); classes 2..6 give the whole CTA (32..512 threads) to one front.
+  int g8_bytes = 4 * 1024, g16_bytes = 8 * 1024;
+  if (const char* e = getenv("SBLX_G8_KB")) g8_bytes = atoi(e) * 1024;       // tuning probes (0 disables the class)
+  if (const char* e = getenv("SBLX_G16_KB")) g16_bytes = atoi(e) * 1024;
+  g8_bytes = std::min(g8_bytes, 12 * 1024);
+  g16_bytes = std::min(g16_bytes, 24 * 1024);
+  int c2_bytes = 72 * 1024;
+  if (const char* e = getenv("SBLX_C2_KB")) c2_bytes = std::min(atoi(e), 80) * 1024;
+  auto front_class_b = [c2_bytes](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= c2_bytes ? 2 : bytes <= 110 * 1024 ? 3 : 4; };
+  auto front_class_p = [&](const Panel& P) {
+    const int bytes = panel_smem_bytes(P.w, P.h);
+    if (P.w <= 4 && bytes <= g8_bytes) return 0;
+    if (P.w <= 8 && bytes <= g16_bytes) return 1;
+    int c = front_class_b(bytes);
+    return 2 + ((P.w > 8 && c < 2) ? 2 : c);
+  };
+  static const int front_nt[7] = {32, 32, 32, 64, 128, 256, 512};
+  static const int front_g[7] = {8, 16, 32, 64, 128, 256, 512};
   std::vector<int> lp;
   h->front_groups.assign(S.nlevels, {});
   h->solve_groups.assign(S.nlevels, {});
@@ -506,6 +523,7 @@ static void upload_model(sblx_handle* h) {
         ++j;
       }
       LaunchGroup g{(int)lp.size() + (int)i, (int)(j - i), front_nt[c], smem};
+      g.lanes = front_g[c];
       for (size_t q = i; q < j; ++q) {
         const Panel& P = S.panels[ids[q]];
         const int hpad = (P.h + 31) & ~31;
@@ -526,6 +544,8 @@ static void upload_model(sblx_handle* h) {
   h->d_level_panels.upload(lp, s);
   CK(cudaStreamSynchronize(s));
   // opt-in shared memory
+  CK(cudaFuncSetAttribute(k_front<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+  CK(cudaFuncSetAttribute(k_front<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
   CK(cudaFuncSetAttribute(k_front<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024));
   CK(cudaFuncSetAttribute(k_front<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
   CK(cudaFuncSetAttribute(k_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
@@ -922,14 +942,16 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   h->ran = false;
 }
 
-template <int NT>
+template <int NT, int G = NT>
 static void launch_front(sblx_handle* h, const LaunchGroup& g, int nstep) {
-  dim3 grid = SBLX_SWAP ? dim3(nstep, g.cnt) : dim3(g.cnt, nstep);
-  k_front<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+  constexpr int NG = NT / G;                       // scenarios per CTA
+  const int stride = (g.smem + 15) / 16;           // double2 per scenario group
+  dim3 grid((nstep + NG - 1) / NG, g.cnt);
+  k_front<NT, G><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off, stride);
 }
 template <int NT>
 static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
-  dim3 grid = SBLX_SWAP ? dim3(nstep, g.cnt) : dim3(g.cnt, nstep);
+  dim3 grid(nstep, g.cnt);
   k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
 }
 
@@ -941,7 +963,11 @@ static void launch_factor(sblx_handle* h, int nstep) {
     if (h->opt.factor_mode != 1) {
       for (const LaunchGroup& g : h->front_groups[l]) {
         switch (g.nt) {
-          case 32: launch_front<32>(h, g, nstep); break;
+          case 32:
+            if (g.lanes == 8) launch_front<32, 8>(h, g, nstep);
+            else if (g.lanes == 16) launch_front<32, 16>(h, g, nstep);
+            else launch_front<32>(h, g, nstep);
+            break;
           case 64: launch_front<64>(h, g, nstep); break;
           case 128: launch_front<128>(h, g, nstep); break;
           case 256: launch_front<256>(h, g, nstep); break;

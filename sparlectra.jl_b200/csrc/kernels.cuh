@@ -538,25 +538,32 @@ __device__ __forceinline__ void bmsub(double2& t0, double2& t1, double2 a0, doub
   t1.y = fma(-a1.x, u0.y, t1.y); t1.y = fma(-a1.y, u1.y, t1.y);
 }
 
-#ifndef SBLX_OCC32
-#define SBLX_OCC32 16
+// Grid: x = scenario (fastest: co-resident CTAs run the SAME front of different scenarios, so the shared index
+// lists hit L1 and the warps follow one code path), y = front of this launch group.
+// G = lanes per scenario.  G == NT: the whole CTA works on one (front, scenario).  G < NT (one-warp CTAs only):
+// the warp is split into NT/G lane groups, each factoring the same small front of a DIFFERENT scenario in its own
+// slice of shared memory - tiny fronts (w <= G/2 pivots) leave most of a warp idle otherwise, and the per-front
+// instruction overhead is shared by the groups.
+template <int NT, int G = NT>
+#ifndef SBLX_OCC128
+#define SBLX_OCC128 3
 #endif
-#ifndef SBLX_OCC64
-#define SBLX_OCC64 10
-#endif
-#ifndef SBLX_SWAP
-#define SBLX_SWAP 1   // scenario = fastest grid dimension: co-resident CTAs run the SAME front of different scenarios (shared index lists hit L1, one code path)
-#endif
-template <int NT>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 ? SBLX_OCC64 : NT == 32 ? SBLX_OCC32 : 1)) k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
-  extern __shared__ double2 sm2[];
-  const int bpanel = SBLX_SWAP ? blockIdx.y : blockIdx.x, bscen = SBLX_SWAP ? blockIdx.x : blockIdx.y;
-  const int panel = panel_ids[bpanel];
-  if (bscen >= L.counts[2]) return;
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? SBLX_OCC128 : NT == 64 ? 10 : NT == 32 ? (G < 32 ? 8 : 16) : 1))
+k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int group_stride) {
+  static_assert(G == NT || NT == 32, "lane groups need a one-warp CTA");
+  extern __shared__ double2 sm2_all[];
+  constexpr int NG = NT / G;
+  const int nact = L.counts[2];
+  if ((int)blockIdx.x * NG >= nact) return;
+  // a group past the end repeats the last scenario (identical values to identical addresses): no predication needed
+  const int bscen = min((int)blockIdx.x * NG + (int)threadIdx.x / G, nact - 1);
+  const int panel = panel_ids[blockIdx.y];
   const int slot = L.step[bscen];
   const PanelDev P = M.panels[panel];
   const int w = P.w, h = P.h, nf = w + h;
-  const int tid = threadIdx.x;
+  const int tid = G == NT ? (int)threadIdx.x : (int)threadIdx.x % G;    // thread index within the scenario's group
+  double2* sm2 = sm2_all + (G == NT ? 0 : ((int)threadIdx.x / G) * group_stride);
+  auto front_sync = [&]() { if (NT == 32) __syncwarp(); else __syncthreads(); };
 #ifdef SBLX_PHASE_TIMING
   long long tmark_ = clock64();
 #endif
@@ -610,13 +617,13 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
     if (v1) { if (k1 < nT) { T0[k1] = y0; T1[k1] = y1; } else { L0[k1 - nT] = y0; L1[k1 - nT] = y1; } }
   };
   {
-    for (int t = tid; t < w * w; t += NT) {            // pivot block: rows i < w, columns j < w
+    for (int t = tid; t < w * w; t += G) {            // pivot block: rows i < w, columns j < w
       const int i = t / w, j = t - i * w;
       ingest_block(i * nf + j);
     }
     const double2* r = A.rhs + (size_t)slot * M.m + P.first;
     const int* vptr = M.vec_ptr + P.first;
-    for (int p = tid; p < w; p += NT) {
+    for (int p = tid; p < w; p += G) {
       double2 v = r[p];
       for (int q = vptr[p]; q < vptr[p + 1]; ++q) v = cadd(v, Ca[M.vec_src[q]]);
       b1[p] = v;
@@ -642,13 +649,14 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
   // __shfl_sync for the trailing update - no shared-memory round trips on the serial chain.
   double2* Dv0 = b1 + w;
   double2* Dv1 = Dv0 + w;
-  __syncthreads();
+  front_sync();
   PHASE_MARK(0);   // ingest of the pivot block
   if (NT > 32 && tid >= 32) ingest_rest(tid - 32, NT - 32);
-  if (tid < 32) {
-    const int lane = tid;
+  if (NT == 32 || tid < 32) {
+    const int lane = tid;                        // lane within the scenario's group: shuffles below use width G
     const int bc = lane >> 1, hi = lane & 1;
-    constexpr int WR = (NT <= 64) ? 8 : 16;      // small classes only hold fronts with w <= 8 (host class rule)
+    constexpr int SW = G < 32 ? G : 32;          // shuffle width
+    constexpr int WR = G < 32 ? G / 2 : (NT <= 64) ? 8 : 16;   // register column (host class rule: w <= WR)
     double a[2 * WR];
 #pragma unroll
     for (int bi = 0; bi < WR; ++bi) {
@@ -671,8 +679,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
     for (int p = 0; p < w; ++p) {
       const int l0 = 2 * p, l1 = 2 * p + 1;
       __syncwarp(full);      // lanes may still be diverged after the data-dependent ingest loops / predicated stores
-      const double p00 = __shfl_sync(full, a[0], l0), p01 = __shfl_sync(full, a[0], l1);
-      const double p10 = __shfl_sync(full, a[1], l0), p11 = __shfl_sync(full, a[1], l1);
+      const double p00 = __shfl_sync(full, a[0], l0, SW), p01 = __shfl_sync(full, a[0], l1, SW);
+      const double p10 = __shfl_sync(full, a[1], l0, SW), p11 = __shfl_sync(full, a[1], l1, SW);
       // det = p00*p11 - p01*p10 with the rounding error of the product recovered by FMA (Kahan)
       const double wq = p01 * p10;
       const double det = fma(p00, p11, -wq) + fma(-p01, p10, wq);
@@ -698,7 +706,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
 #pragma unroll
       for (int j = 2; j < 2 * WR; ++j) {
         if (j < rem) {
-          const double m0 = __shfl_sync(full, a[j], l0), m1 = __shfl_sync(full, a[j], l1);
+          const double m0 = __shfl_sync(full, a[j], l0, SW), m1 = __shfl_sync(full, a[j], l1, SW);
           if (right) a[j] = fma(-m1, u1, fma(-m0, u0, a[j]));
         }
       }
@@ -709,14 +717,15 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
     }
     if (sing && lane == 0) atomicOr(&A.singular[slot], 1);
     PHASE_MARK(1);   // pivot-block chain (warp 0)
-    if (NT == 32) ingest_rest(tid, NT);
+    if (NT == 32) ingest_rest(tid, G);
   }
-  __syncthreads();
+  front_sync();
   // ---- step 2: independent substitution tasks, no barriers: U'12 columns (and the rhs) against the
   // multipliers of the pivot block, L21 rows against the scaled pivot rows.
   {
-    const int hpad = (h + 1 + 31) & ~31;            // column tasks: h structure columns + the rhs
-    for (int t = tid; t < 2 * hpad; t += NT) {
+    constexpr int TP = G < 32 ? G : 32;             // task padding: a warp (or lane group) never mixes task kinds
+    const int hpad = (h + 1 + TP - 1) & ~(TP - 1);  // column tasks: h structure columns + the rhs
+    for (int t = tid; t < 2 * hpad; t += G) {
       if (t < hpad) {
         const int b = t;
         if (b < h) {
@@ -760,14 +769,14 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
       }
     }
   }
-  __syncthreads();
+  front_sync();
   PHASE_MARK(2);   // wait for substitution tasks
   // ---- store U' panel and y'
   {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
-    for (int i = tid; i < nT; i += NT) { U[2 * i] = T0[i]; U[2 * i + 1] = T1[i]; }
+    for (int i = tid; i < nT; i += G) { U[2 * i] = T0[i]; U[2 * i + 1] = T1[i]; }
     double2* y = A.yv + (size_t)slot * M.m + P.first;
-    for (int p = tid; p < w; p += NT) y[p] = b1[p];
+    for (int p = tid; p < w; p += G) y[p] = b1[p];
   }
   PHASE_MARK(3);   // U store issue
   if (h == 0) return;
@@ -843,7 +852,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
   } else {
     // small fronts: one 2x2-block register tile per thread
     const int th = (h + 1) >> 1;
-    for (int tile = tid; tile < th * th; tile += NT) {
+    for (int tile = tid; tile < th * th; tile += G) {
       const int a0 = (tile / th) * 2, b0 = (tile % th) * 2;
       const bool va = a0 + 1 < h, vb = b0 + 1 < h;
       double2 acc[2][2][2];
@@ -885,7 +894,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
   PHASE_MARK(4);   // Schur (thread 0's share)
   // ---- update vector: cv[a] = gather(children) - L[a][:] y'
   double2* cvo = Co + 2 * (size_t)h * h;
-  for (int a = tid; a < h; a += NT) {
+  for (int a = tid; a < h; a += G) {
     double2 v = make_double2(0.0, 0.0);
     for (int p = 0; p < w; ++p) {
       const double2 l0 = L0[p * h + a], l1 = L1[p * h + a], y = b1[p];
@@ -904,7 +913,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? 3 : NT == 64 
   }
   PHASE_MARK(5);
 #ifdef SBLX_PHASE_TIMING
-  __syncthreads();
+  front_sync();
   PHASE_MARK(6);   // tail: slowest warp
 #endif
 #ifdef SBLX_PHASE_TIMING
@@ -1238,10 +1247,9 @@ __global__ void __launch_bounds__(128, 4) k_schur(DevModel M, Slots A, Lists L, 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
   extern __shared__ double2 sm2[];
-  const int bpanel = SBLX_SWAP ? blockIdx.y : blockIdx.x, bscen = SBLX_SWAP ? blockIdx.x : blockIdx.y;
-  const int panel = panel_ids[bpanel];
-  if (bscen >= L.counts[2]) return;
-  const int slot = L.step[bscen];
+  const int panel = panel_ids[blockIdx.y];              // grid: x = scenario (fastest), y = front
+  if ((int)blockIdx.x >= L.counts[2]) return;
+  const int slot = L.step[blockIdx.x];
   const PanelDev P = M.panels[panel];
   const int w = P.w, h = P.h, nf = w + h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

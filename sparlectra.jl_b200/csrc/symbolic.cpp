@@ -55,7 +55,8 @@ static void order_md(const Adj& adj_in, std::vector<int>& order) {
 struct NdCtx {
   const Adj* adj;
   std::vector<int> tag;    // subset membership stamp
-  std::vector<int> lvl;
+  std::vector<int> lvl, lvl2, side;
+  bool use_fband = true;
   int stamp = 0;
   int leaf = 48;
   std::vector<int>* out;
@@ -128,7 +129,7 @@ static void nd_rec(NdCtx& c, std::vector<int> S) {
     for (int v : ord) c.tag[v] = st;  // restore membership stamp
   };
   std::vector<int> ord;
-  int root = S[0];
+  int root = S[0], far = S[0];
   int depth = -1;
   for (int rep = 0; rep < 4; ++rep) {  // pseudo-peripheral node
     bfs(root, ord);
@@ -140,63 +141,111 @@ static void nd_rec(NdCtx& c, std::vector<int> S) {
       if (adj[ord[i]].size() < adj[best].size()) best = ord[i];
     if (L <= depth) break;
     depth = L;
+    far = root;
     root = best;
   }
+  // Two separator families are tried and the smaller (balance-weighted, after trimming) one is kept:
+  //  (1) a level of the BFS level structure rooted at the pseudo-peripheral node p (George's automatic ND);
+  //  (2) a band {c, c+1} of f(v) = d(p, v) - d(q, v), q = the far end of the pseudo-diameter.  |f(u) - f(v)| <= 2
+  //      along an edge, so two consecutive values always separate; on mesh-like grids the level sets of f run
+  //      ACROSS the diameter and are much shorter than the ring-shaped BFS levels.
+  const int total = (int)S.size();
+  bfs(far, ord);
+  std::vector<int> dq(total);
+  for (int i = 0; i < total; ++i) c.lvl2[S[i]] = c.lvl[S[i]];
   bfs(root, ord);
   const int nl = c.lvl[ord.back()] + 1;
   if (nl < 3) {  // (near-)clique: no useful separator
     nd_leaf_md(c, S);
     return;
   }
-  std::vector<int> cnt(nl, 0);
-  for (int v : ord) cnt[c.lvl[v]]++;
-  const int total = (int)S.size();
-  int bestl = -1;
-  double bestscore = 1e300;
-  int cum = 0;
-  for (int l = 0; l < nl; ++l) {
-    int left = cum, right = total - cum - cnt[l];
-    cum += cnt[l];
-    if (l == 0 || l == nl - 1) continue;
-    double bal = (double)std::min(left, right) / std::max(1, std::max(left, right));
-    if (bal < 0.35) continue;
-    double score = cnt[l] / (0.2 + bal);
-    if (score < bestscore) {
-      bestscore = score;
-      bestl = l;
+  auto pick = [&](const std::vector<int>& cnt, int width, int& bestk, double& bestscore) {
+    // cnt[k] = members with key k; separator = keys [k, k + width); returns the best k by size / balance
+    const int nk = (int)cnt.size();
+    bestk = -1;
+    bestscore = 1e300;
+    int cum = 0;
+    for (int k = 0; k + width <= nk; ++k) {
+      int sep = 0;
+      for (int j = 0; j < width; ++j) sep += cnt[k + j];
+      const int left = cum, right = total - cum - sep;
+      cum += cnt[k];
+      if (left == 0 || right == 0) continue;
+      const double bal = (double)std::min(left, right) / std::max(1, std::max(left, right));
+      if (bal < 0.35) continue;
+      const double score = sep / (0.2 + bal);
+      if (score < bestscore) {
+        bestscore = score;
+        bestk = k;
+      }
     }
+  };
+  // key arrays: family 1 = level, family 2 = f shifted to >= 0
+  std::vector<int> cnt1(nl, 0);
+  for (int v : ord) cnt1[c.lvl[v]]++;
+  int fmin = 1 << 30, fmax = -(1 << 30);
+  for (int v : ord) {
+    const int f = c.lvl[v] - c.lvl2[v];
+    fmin = std::min(fmin, f);
+    fmax = std::max(fmax, f);
   }
-  if (bestl < 0) {
+  std::vector<int> cnt2(fmax - fmin + 1, 0);
+  for (int v : ord) cnt2[c.lvl[v] - c.lvl2[v] - fmin]++;
+  int k1, k2;
+  double s1, s2;
+  pick(cnt1, 1, k1, s1);
+  pick(cnt2, 2, k2, s2);
+  if (k1 < 0) {
     int cum2 = 0;
     for (int l = 0; l < nl; ++l) {
-      cum2 += cnt[l];
+      cum2 += cnt1[l];
       if (cum2 * 2 >= total) {
-        bestl = std::min(std::max(l, 1), nl - 2);
+        k1 = std::min(std::max(l, 1), nl - 2);
         break;
       }
     }
   }
-  std::vector<int> A, B, Sep;
-  for (int v : ord) {
-    int l = c.lvl[v];
-    if (l < bestl)
-      A.push_back(v);
-    else if (l > bestl)
-      B.push_back(v);
-    else {
-      bool touches = false;
-      for (int u : adj[v])
-        if (c.tag[u] == st && c.lvl[u] == bestl + 1) {
-          touches = true;
-          break;
-        }
-      (touches ? Sep : A).push_back(v);
+  // materialise a candidate: side[v] in c.side: 0 = A, 1 = separator, 2 = B; trimmed on both faces
+  auto build = [&](int family, int k, std::vector<int>& A, std::vector<int>& B, std::vector<int>& Sep) -> double {
+    A.clear(); B.clear(); Sep.clear();
+    if (k < 0) return 1e300;
+    const int width = family == 1 ? 1 : 2;
+    for (int v : ord) {
+      const int key = family == 1 ? c.lvl[v] : c.lvl[v] - c.lvl2[v] - fmin;
+      c.side[v] = key < k ? 0 : key >= k + width ? 2 : 1;
     }
+    for (int v : ord)      // separator nodes that do not touch B fall back to A
+      if (c.side[v] == 1) {
+        bool t = false;
+        for (int u : adj[v])
+          if (c.tag[u] == st && c.side[u] == 2) { t = true; break; }
+        if (!t) c.side[v] = 0;
+      }
+    for (int v : ord)      // ... and those that do not touch A (any more) go to B
+      if (c.side[v] == 1) {
+        bool t = false;
+        for (int u : adj[v])
+          if (c.tag[u] == st && c.side[u] == 0) { t = true; break; }
+        if (!t) c.side[v] = 2;
+      }
+    for (int v : ord) (c.side[v] == 0 ? A : c.side[v] == 2 ? B : Sep).push_back(v);
+    if (A.empty() || B.empty()) return 1e300;
+    const double bal = (double)std::min(A.size(), B.size()) / std::max(A.size(), B.size());
+    return Sep.size() / (0.2 + bal);
+  };
+  std::vector<int> A, B, Sep, A2, B2, Sep2;
+  const double f1 = build(1, k1, A, B, Sep);
+  const double f2 = c.use_fband ? build(2, k2, A2, B2, Sep2) : 1e300;
+  if (f2 < f1) {
+    A.swap(A2);
+    B.swap(B2);
+    Sep.swap(Sep2);
   }
   if (A.empty() || B.empty()) {
     nd_leaf_md(c, S);
     return;
   }
+  if (getenv("SBLX_ND_DEBUG") && total > 600) fprintf(stderr, "nd: |S|=%d -> A=%zu B=%zu Sep=%zu (level %.1f, fband %.1f)\n", total, A.size(), B.size(), Sep.size(), f1, f2);
   std::vector<int> sepcopy = Sep;
   nd_rec(c, std::move(A));
   nd_rec(c, std::move(B));
@@ -209,6 +258,9 @@ static void order_nd(const Adj& adj, int leaf, std::vector<int>& order) {
   c.adj = &adj;
   c.tag.assign(n, 0);
   c.lvl.assign(n, 0);
+  c.lvl2.assign(n, 0);
+  c.side.assign(n, 0);
+  c.use_fband = getenv("SBLX_ND_NO_FBAND") == nullptr;
   c.leaf = leaf;
   order.clear();
   order.reserve(n);
