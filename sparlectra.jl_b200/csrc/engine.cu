@@ -363,7 +363,7 @@ struct sblx_handle {
   DevBuf<unsigned char> d_type0, d_lock, d_br_status;
   DevBuf<int> d_br_from, d_br_to;
   DevBuf<PanelDev> d_panels;
-  DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels, d_ing_ptr, d_ing_src, d_vec_ptr, d_vec_src;
+  DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels, d_ing_ptr, d_ing_src, d_ing_pairs, d_ing_xptr, d_ing_xsrc, d_vec_ptr, d_vec_src;
   DevBuf<ChildDev> d_childdev;
   DevBuf<long long> d_rel_ptr, d_inv_ptr;
   std::vector<std::vector<LaunchGroup>> front_groups;   // per level
@@ -458,7 +458,7 @@ static void upload_model(sblx_handle* h) {
   std::vector<PanelDev> pd(S.panels.size());
   for (size_t i = 0; i < pd.size(); ++i) {
     const Panel& P = S.panels[i];
-    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.ing_base, l_off[i], (long long)P.u_off, (long long)P.c_off};
+    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.ing_base, l_off[i], (long long)P.u_off, (long long)P.c_off, (int)P.ingf_base};
   }
   h->d_panels.upload(pd, s);
   h->d_struct.upload(S.struct_nodes, s);
@@ -470,6 +470,9 @@ static void upload_model(sblx_handle* h) {
   h->d_asm_dst.upload(S.asm_dst, s);
   h->d_ing_ptr.upload(S.ing_ptr, s);
   h->d_ing_src.upload(S.ing_src, s);
+  h->d_ing_pairs.upload(S.ing_pairs, s);
+  h->d_ing_xptr.upload(S.ing_xptr, s);
+  h->d_ing_xsrc.upload(S.ing_xsrc.empty() ? std::vector<int>(1, 0) : S.ing_xsrc, s);
   h->d_vec_ptr.upload(S.vec_ptr, s);
   h->d_vec_src.upload(S.vec_src, s);
   {
@@ -570,7 +573,8 @@ static void upload_model(sblx_handle* h) {
   M.panels = h->d_panels.p; M.struct_nodes = h->d_struct.p; M.child_list = h->d_child.p; M.rel = h->d_rel.p;
   M.rel_ptr = h->d_rel_ptr.p; M.kpiv = h->d_kpiv.p; M.inv = h->d_inv.p; M.inv_ptr = h->d_inv_ptr.p;
   M.asm_src = h->d_asm_src.p; M.asm_dst = h->d_asm_dst.p;
-  M.ing_ptr = h->d_ing_ptr.p; M.ing_src = h->d_ing_src.p; M.vec_ptr = h->d_vec_ptr.p; M.vec_src = h->d_vec_src.p;
+  M.ing_ptr = h->d_ing_ptr.p; M.ing_src = h->d_ing_src.p;
+  M.ing_pairs = reinterpret_cast<const int2*>(h->d_ing_pairs.p); M.ing_xptr = h->d_ing_xptr.p; M.ing_xsrc = h->d_ing_xsrc.p; M.vec_ptr = h->d_vec_ptr.p; M.vec_src = h->d_vec_src.p;
   M.childdev = h->d_childdev.p;
   M.u_blocks = S.u_blocks; M.c_blocks = S.c_blocks + 2; M.l_blocks = h->l_blocks;
   const sblx_options& o = h->opt;
@@ -1518,14 +1522,14 @@ int sblx_solve_one(sblx_handle* h, const double* v_start, double* v_out, uint8_t
   API_END(h)
 }
 
-int sblx_debug_phase_cycles(double* out40) {
+int sblx_debug_phase_cycles(double* out50) {
 #ifdef SBLX_PHASE_TIMING
-  unsigned long long hbuf[40];
+  unsigned long long hbuf[50];
   if (cudaMemcpyFromSymbol(hbuf, g_phase_cycles, sizeof hbuf) != cudaSuccess) return SBLX_E_CUDA;
-  for (int i = 0; i < 40; ++i) out40[i] = (double)hbuf[i];
+  for (int i = 0; i < 50; ++i) out50[i] = (double)hbuf[i];
   return SBLX_OK;
 #else
-  (void)out40;
+  (void)out50;
   return SBLX_E_ARG;
 #endif
 }

@@ -23,6 +23,7 @@
 
 namespace sblx {
 
+constexpr int ING_NONE = INT32_MIN, ING_MULTI = 1 << 30;   // ingest word encoding (same constants in symbolic.h)
 constexpr int MAXOUT = 8;          // outaged branches per scenario (N-k, k <= 8)
 constexpr int ST_IDLE = 0, ST_RUN = 1, ST_DRAIN = 2;
 constexpr int T_ISO = 0, T_PQ = 1, T_PV = 2, T_SLACK = 3;
@@ -31,6 +32,7 @@ struct PanelDev {
   int first, w, h, nchild;
   int struct_ptr, child_ptr, ing_base, l_off;   // l_off: level-local offset (blocks) of this panel's L21 in the Lw workspace
   long long u_off, c_off;
+  int ingf_base, pad_;
 };
 // per (parent, child) record used by the Schur gather
 struct ChildDev {
@@ -49,7 +51,7 @@ struct DevModel {
   const double* rating; const unsigned char* br_status;
   const PanelDev* panels; const int* struct_nodes; const int* child_list; const int* rel; const long long* rel_ptr;
   const int* kpiv; const int* inv; const long long* inv_ptr; const int* asm_src; const int* asm_dst;
-  const int* ing_ptr; const int* ing_src; const int* vec_ptr; const int* vec_src; const ChildDev* childdev;
+  const int* ing_ptr; const int* ing_src; const int2* ing_pairs; const int* ing_xptr; const int* ing_xsrc; const int* vec_ptr; const int* vec_src; const ChildDev* childdev;
   long long u_blocks, c_blocks, l_blocks;
   double tol, damp, hyst, vm_min, vm_max, base_mva;
   int max_iter, qlim_enabled, qlim_start, cooldown, guard, freeze, allow_reenable;
@@ -89,6 +91,18 @@ struct Batch {
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+// One 2x2 block (32 B, 32 B aligned) per instruction: sm_100 has 256-bit global loads / stores (LDG.256 / STG.256),
+// so a block is one full DRAM sector per thread and instruction instead of two half-sector accesses.
+__device__ __forceinline__ void ldg_blk(const double2* p, double2& r0, double2& r1) {
+#ifndef SBLX_LDG_ALLOC   // streamed once: keep L1 for the index lists shared by the co-resident CTAs
+  asm("ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r0.x), "=d"(r0.y), "=d"(r1.x), "=d"(r1.y) : "l"(__cvta_generic_to_global(p)));
+#else
+  asm("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r0.x), "=d"(r0.y), "=d"(r1.x), "=d"(r1.y) : "l"(__cvta_generic_to_global(p)));
+#endif
+}
+__device__ __forceinline__ void stg_blk(double2* p, double2 r0, double2 r1) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "d"(r0.x), "d"(r0.y), "d"(r1.x), "d"(r1.y) : "memory");
+}
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ unsigned long long abs_bits(double x) { return (unsigned long long)__double_as_longlong(fabs(x)); }
 __device__ __forceinline__ double bits_double(unsigned long long b) { return __longlong_as_double((long long)b); }
@@ -494,12 +508,11 @@ __global__ void __launch_bounds__(256) k_jacobian(DevModel M, Slots A, Lists L) 
     }
   }
   double2* out = reinterpret_cast<double2*>(A.Jv + ((size_t)slot * M.nnzB + ent) * 4);
-  out[0] = make_double2(b00, b01);
-  out[1] = make_double2(b10, b11);
+  stg_blk(out, make_double2(b00, b01), make_double2(b10, b11));
 }
 
 #ifdef SBLX_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[5][8];   // [class][phase]
+__device__ unsigned long long g_phase_cycles[5][10];   // [class][phase]; [9] = CTA count
 #define PHASE_MARK(ph)                                                                             \
   do {                                                                                             \
     if (threadIdx.x == 0) {                                                                        \
@@ -545,6 +558,9 @@ __device__ __forceinline__ void bmsub(double2& t0, double2& t1, double2 a0, doub
 // slice of shared memory - tiny fronts (w <= G/2 pivots) leave most of a warp idle otherwise, and the per-front
 // instruction overhead is shared by the groups.
 template <int NT, int G = NT>
+#ifndef SBLX_INGEST_BATCH
+#define SBLX_INGEST_BATCH 2
+#endif
 #ifndef SBLX_OCC128
 #define SBLX_OCC128 3
 #endif
@@ -582,45 +598,46 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
   // multi-warp CTA it is done by warps 1.. WHILE warp 0 factors the pivot block in registers.
   const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
   const double2* Ca = reinterpret_cast<const double2*>(Cs);
-  const int* iptr = M.ing_ptr + P.ing_base;
-  const int* isrc = M.ing_src;
-  auto ingest_block = [&](int k) {
-    double2 x0 = make_double2(0.0, 0.0), x1 = x0;
-    const int s0 = iptr[k], e0 = iptr[k + 1];
-    for (int q = s0; q < e0; ++q) {
-      const int sidx = isrc[q];
-      const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
-      x0 = cadd(x0, ptr[0]); x1 = cadd(x1, ptr[1]);
-    }
+  const int2* ipairs = M.ing_pairs + P.ingf_base;       // (source word, shared-memory block index), in walk order
+  auto store_block = [&](int k, double2 x0, double2 x1) {
     if (k < nT) { T0[k] = x0; T1[k] = x1; } else { L0[k - nT] = x0; L1[k - nT] = x1; }
   };
-  auto ingest_pair = [&](int k0, int k1, bool v1) {     // two blocks with interleaved (independent) source loads
-    const int s0 = iptr[k0], e0 = iptr[k0 + 1];
-    const int s1 = v1 ? iptr[k1] : 0, e1 = v1 ? iptr[k1 + 1] : 0;
-    double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
-    int q0 = s0, q1 = s1;
-    while (q0 < e0 || q1 < e1) {
-      double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1v = a0;
-      if (q0 < e0) {
-        const int sidx = isrc[q0++];
-        const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
-        a0 = ptr[0]; a1 = ptr[1];
+  // IB panel blocks per thread and step: the IB index pairs are loaded first, then all value loads are in flight
+  // together (single-source blocks: one dependent load level); multi-source blocks (8 %) take the CSR side path.
+  constexpr int IB = SBLX_INGEST_BATCH;
+  auto ingest_range = [&](int lo, int hi, int t0, int tstep) {
+    for (int t = lo + t0; t < hi; t += IB * tstep) {
+      int2 e[IB];
+#pragma unroll
+      for (int i = 0; i < IB; ++i) e[i] = (t + i * tstep < hi) ? ipairs[t + i * tstep] : make_int2(ING_NONE, -1);
+      double2 x0[IB], x1[IB];
+#pragma unroll
+      for (int i = 0; i < IB; ++i) {
+        const int v = e[i].x;
+        const double2* ptr = v < 0 ? Jv + 2 * (size_t)(~v) : Ca + 2 * (size_t)v;
+        x0[i] = make_double2(0.0, 0.0);
+        x1[i] = x0[i];
+        if (v != ING_NONE && v < ING_MULTI) ldg_blk(ptr, x0[i], x1[i]);
       }
-      if (q1 < e1) {
-        const int sidx = isrc[q1++];
-        const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
-        b0 = ptr[0]; b1v = ptr[1];
-      }
-      x0 = cadd(x0, a0); x1 = cadd(x1, a1); y0 = cadd(y0, b0); y1 = cadd(y1, b1v);
+#pragma unroll
+      for (int i = 0; i < IB; ++i)
+        if (e[i].x >= ING_MULTI) {
+          const int x = e[i].x - ING_MULTI;
+          for (int q = M.ing_xptr[x]; q < M.ing_xptr[x + 1]; ++q) {
+            const int sidx = M.ing_xsrc[q];
+            const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+            double2 s0, s1;
+            ldg_blk(ptr, s0, s1);
+            x0[i] = cadd(x0[i], s0); x1[i] = cadd(x1[i], s1);
+          }
+        }
+#pragma unroll
+      for (int i = 0; i < IB; ++i)
+        if (e[i].y >= 0) store_block(e[i].y, x0[i], x1[i]);
     }
-    if (k0 < nT) { T0[k0] = x0; T1[k0] = x1; } else { L0[k0 - nT] = x0; L1[k0 - nT] = x1; }
-    if (v1) { if (k1 < nT) { T0[k1] = y0; T1[k1] = y1; } else { L0[k1 - nT] = y0; L1[k1 - nT] = y1; } }
   };
   {
-    for (int t = tid; t < w * w; t += G) {            // pivot block: rows i < w, columns j < w
-      const int i = t / w, j = t - i * w;
-      ingest_block(i * nf + j);
-    }
+    ingest_range(0, w * w, tid, G);                     // the pivot block
     const double2* r = A.rhs + (size_t)slot * M.m + P.first;
     const int* vptr = M.vec_ptr + P.first;
     for (int p = tid; p < w; p += G) {
@@ -629,19 +646,8 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
       b1[p] = v;
     }
   }
-  // the rest of the panel: T columns j >= w of every pivot row, then all structure-row blocks
-  auto ingest_rest = [&](int t0, int tstep) {
-    const int nTr = w * h;                               // T blocks right of the pivot block
-    const int nrest = nTr + nL;
-    for (int t = t0; t < nrest; t += 2 * tstep) {
-      const int u = t + tstep;
-      const bool v1 = u < nrest;
-      int k0, k1 = 0;
-      if (t < nTr) { const int i = t / h, j = t - i * h; k0 = i * nf + w + j; } else k0 = nT + (t - nTr);
-      if (v1) { if (u < nTr) { const int i = u / h, j = u - i * h; k1 = i * nf + w + j; } else k1 = nT + (u - nTr); }
-      ingest_pair(k0, k1, v1);
-    }
-  };
+  // the rest of the panel: the pivot rows right of the pivot block, then all structure-row blocks
+  auto ingest_rest = [&](int t0, int tstep) { ingest_range(w * w, nT + nL, t0, tstep); };
   // ---- panel factorisation, step 1: the pivot block (w <= 16 bus blocks = at most 32 x 32 scalars) is
   // factored entirely in the registers of warp 0: lane = scalar column, a[i] = scalar row i of that
   // column; per 2x2 pivot the inverse is formed once, the two pivot rows are scaled in place
@@ -720,6 +726,7 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
     if (NT == 32) ingest_rest(tid, G);
   }
   front_sync();
+  PHASE_MARK(2);   // barrier after the chain: the other warps' share of the ingest
   // ---- step 2: independent substitution tasks, no barriers: U'12 columns (and the rhs) against the
   // multipliers of the pivot block, L21 rows against the scaled pivot rows.
   {
@@ -770,15 +777,15 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
     }
   }
   front_sync();
-  PHASE_MARK(2);   // wait for substitution tasks
+  PHASE_MARK(3);   // substitution tasks
   // ---- store U' panel and y'
   {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
-    for (int i = tid; i < nT; i += G) { U[2 * i] = T0[i]; U[2 * i + 1] = T1[i]; }
+    for (int i = tid; i < nT; i += G) stg_blk(U + 2 * i, T0[i], T1[i]);
     double2* y = A.yv + (size_t)slot * M.m + P.first;
     for (int p = tid; p < w; p += G) y[p] = b1[p];
   }
-  PHASE_MARK(3);   // U store issue
+  PHASE_MARK(4);   // U store issue
   if (h == 0) return;
   double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
   // ---- Schur complement straight to HBM: C = gather(children) - L * U'
@@ -833,8 +840,9 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
           const double2* spA = Cm + 2 * ((size_t)(okA ? ia[i] : 0) * hc + (okA ? ibA : 0));
           const double2* spB = Cm + 2 * ((size_t)(okB ? ia[i] : 0) * hc + (okB ? ibB : 0));
           const double2 z = make_double2(0.0, 0.0);
-          g[i][0][0] = okA ? spA[0] : z; g[i][0][1] = okA ? spA[1] : z;
-          g[i][1][0] = okB ? spB[0] : z; g[i][1][1] = okB ? spB[1] : z;
+          g[i][0][0] = z; g[i][0][1] = z; g[i][1][0] = z; g[i][1][1] = z;
+          if (okA) ldg_blk(spA, g[i][0][0], g[i][0][1]);
+          if (okB) ldg_blk(spB, g[i][1][0], g[i][1][1]);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -845,8 +853,8 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (a0 + i >= h) break;
-        if (vA) { Co[2 * ((a0 + i) * h + bA)] = acc[i][0][0]; Co[2 * ((a0 + i) * h + bA) + 1] = acc[i][0][1]; }
-        if (vB) { Co[2 * ((a0 + i) * h + bB)] = acc[i][1][0]; Co[2 * ((a0 + i) * h + bB) + 1] = acc[i][1][1]; }
+        if (vA) stg_blk(Co + 2 * ((a0 + i) * h + bA), acc[i][0][0], acc[i][0][1]);
+        if (vB) stg_blk(Co + 2 * ((a0 + i) * h + bB), acc[i][1][0], acc[i][1][1]);
       }
     }
   } else {
@@ -878,20 +886,20 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
         const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
         const int ia0 = inv[a0], ia1 = va ? inv[a0 + 1] : -1;
         const int ib0 = inv[b0], ib1 = vb ? inv[b0 + 1] : -1;
-        if (ia0 >= 0 && ib0 >= 0) { const double2* sp = Cm + 2 * (ia0 * hc + ib0); acc[0][0][0] = cadd(acc[0][0][0], sp[0]); acc[0][0][1] = cadd(acc[0][0][1], sp[1]); }
-        if (ia0 >= 0 && ib1 >= 0) { const double2* sp = Cm + 2 * (ia0 * hc + ib1); acc[0][1][0] = cadd(acc[0][1][0], sp[0]); acc[0][1][1] = cadd(acc[0][1][1], sp[1]); }
-        if (ia1 >= 0 && ib0 >= 0) { const double2* sp = Cm + 2 * (ia1 * hc + ib0); acc[1][0][0] = cadd(acc[1][0][0], sp[0]); acc[1][0][1] = cadd(acc[1][0][1], sp[1]); }
-        if (ia1 >= 0 && ib1 >= 0) { const double2* sp = Cm + 2 * (ia1 * hc + ib1); acc[1][1][0] = cadd(acc[1][1][0], sp[0]); acc[1][1][1] = cadd(acc[1][1][1], sp[1]); }
+        if (ia0 >= 0 && ib0 >= 0) { double2 s0, s1; ldg_blk(Cm + 2 * (ia0 * hc + ib0), s0, s1); acc[0][0][0] = cadd(acc[0][0][0], s0); acc[0][0][1] = cadd(acc[0][0][1], s1); }
+        if (ia0 >= 0 && ib1 >= 0) { double2 s0, s1; ldg_blk(Cm + 2 * (ia0 * hc + ib1), s0, s1); acc[0][1][0] = cadd(acc[0][1][0], s0); acc[0][1][1] = cadd(acc[0][1][1], s1); }
+        if (ia1 >= 0 && ib0 >= 0) { double2 s0, s1; ldg_blk(Cm + 2 * (ia1 * hc + ib0), s0, s1); acc[1][0][0] = cadd(acc[1][0][0], s0); acc[1][0][1] = cadd(acc[1][0][1], s1); }
+        if (ia1 >= 0 && ib1 >= 0) { double2 s0, s1; ldg_blk(Cm + 2 * (ia1 * hc + ib1), s0, s1); acc[1][1][0] = cadd(acc[1][1][0], s0); acc[1][1][1] = cadd(acc[1][1][1], s1); }
       }
-      Co[2 * (a0 * h + b0)] = acc[0][0][0]; Co[2 * (a0 * h + b0) + 1] = acc[0][0][1];
-      if (vb) { Co[2 * (a0 * h + b0 + 1)] = acc[0][1][0]; Co[2 * (a0 * h + b0 + 1) + 1] = acc[0][1][1]; }
+      stg_blk(Co + 2 * (a0 * h + b0), acc[0][0][0], acc[0][0][1]);
+      if (vb) stg_blk(Co + 2 * (a0 * h + b0 + 1), acc[0][1][0], acc[0][1][1]);
       if (va) {
-        Co[2 * ((a0 + 1) * h + b0)] = acc[1][0][0]; Co[2 * ((a0 + 1) * h + b0) + 1] = acc[1][0][1];
-        if (vb) { Co[2 * ((a0 + 1) * h + b0 + 1)] = acc[1][1][0]; Co[2 * ((a0 + 1) * h + b0 + 1) + 1] = acc[1][1][1]; }
+        stg_blk(Co + 2 * ((a0 + 1) * h + b0), acc[1][0][0], acc[1][0][1]);
+        if (vb) stg_blk(Co + 2 * ((a0 + 1) * h + b0 + 1), acc[1][1][0], acc[1][1][1]);
       }
     }
   }
-  PHASE_MARK(4);   // Schur (thread 0's share)
+  PHASE_MARK(5);   // Schur (thread 0's share)
   // ---- update vector: cv[a] = gather(children) - L[a][:] y'
   double2* cvo = Co + 2 * (size_t)h * h;
   for (int a = tid; a < h; a += G) {
@@ -911,13 +919,13 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
     }
     cvo[a] = v;
   }
-  PHASE_MARK(5);
+  PHASE_MARK(6);
 #ifdef SBLX_PHASE_TIMING
   front_sync();
-  PHASE_MARK(6);   // tail: slowest warp
+  PHASE_MARK(7);   // tail: slowest warp
 #endif
 #ifdef SBLX_PHASE_TIMING
-  if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[NT == 32 ? 0 : NT == 64 ? 1 : NT == 128 ? 2 : NT == 256 ? 3 : 4][7], 1ull);
+  if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[NT == 32 ? 0 : NT == 64 ? 1 : NT == 128 ? 2 : NT == 256 ? 3 : 4][9], 1ull);
 #endif
 }
 

@@ -648,6 +648,9 @@ static void build_from_order(int m, const std::vector<int64_t>& rowptr, const st
   {
     S.ing_ptr.clear();
     S.ing_src.clear();
+    S.ing_pairs.clear();
+    S.ing_xptr.assign(1, 0);
+    S.ing_xsrc.clear();
     S.vec_ptr.assign(m + 1, 0);
     S.vec_src.clear();
     std::vector<std::vector<int>> vsrc(m);
@@ -675,10 +678,31 @@ static void build_from_order(int m, const std::vector<int64_t>& rowptr, const st
         for (int a = 0; a < kc; ++a) vsrc[P.first + rel[a]].push_back((int)(vbase + a));
       }
       P.ing_base = (int64_t)S.ing_ptr.size();
+      P.ingf_base = (int64_t)S.ing_pairs.size() / 2;
       for (int k = 0; k < nblk; ++k) {
         S.ing_ptr.push_back((int)S.ing_src.size());
         for (int v : src[k]) S.ing_src.push_back(v);
       }
+      auto emit = [&](int k) {
+        int word;
+        if (src[k].empty()) word = ING_NONE;
+        else if (src[k].size() == 1) {
+          if (src[k][0] >= ING_MULTI) throw std::runtime_error("sblx symbolic: update arena too large for the ingest encoding");
+          word = src[k][0];
+        } else {
+          word = ING_MULTI + (int)S.ing_xptr.size() - 1;
+          for (int v : src[k]) S.ing_xsrc.push_back(v);
+          S.ing_xptr.push_back((int)S.ing_xsrc.size());
+        }
+        S.ing_pairs.push_back(word);
+        S.ing_pairs.push_back(k);
+      };
+      for (int r = 0; r < w; ++r)
+        for (int c2 = 0; c2 < w; ++c2) emit(r * nf + c2);                 // pivot block
+      for (int r = 0; r < w; ++r)
+        for (int j = 0; j < h; ++j) emit(r * nf + w + j);                 // pivot rows right of it
+      for (int li = 0; li < h; ++li)
+        for (int lj = 0; lj < w; ++lj) emit(w * nf + lj * h + li);       // structure rows, pivot column fastest
       S.ing_ptr.push_back((int)S.ing_src.size());
     }
     for (int e2 = 0; e2 < m; ++e2) {

@@ -37,6 +37,7 @@ struct Panel {
   int64_t child_ptr = 0, nchild = 0;  // into child_list
   int64_t asm_ptr = 0, asm_cnt = 0;   // original Jacobian blocks assembled here
   int64_t ing_base = 0;               // first entry of this panel in ing_ptr (w*(w+h) + h*w + 1 entries)
+  int64_t ingf_base = 0;              // first (source, destination) pair of this panel in ing_pairs (w*(w+h) + h*w pairs)
 };
 
 struct Symbolic {
@@ -59,6 +60,13 @@ struct Symbolic {
   // gather-style ingest: per panel block (shared-memory order: pivot rows [w][nf], then structure rows pivot-major
   // [w][h]) the CSR list of its sources; src < 0: Jacobian slot ~src, src >= 0: block offset in the update arena
   std::vector<int> ing_ptr, ing_src;
+  // the same lists in the form the fused front kernel reads: one (source, destination) pair per panel block IN THE
+  // ORDER THE THREADS WALK (pivot block row-major; pivot rows right of it; structure rows with the pivot column
+  // fastest = along the rows of the children's update matrices), so the kernel does no index arithmetic.
+  // source: ING_NONE (explicit zero), the single source (75 % of the blocks: one dependent index load instead of
+  // two), or ING_MULTI + x with the sources in ing_xsrc[ing_xptr[x] .. ing_xptr[x+1]); destination: block index in
+  // the shared-memory panel
+  std::vector<int> ing_pairs, ing_xptr, ing_xsrc;
   // rhs of the pivots: per elimination index the CSR list of update-vector entries (double2 index in the arena)
   std::vector<int> vec_ptr, vec_src;
   // levels
@@ -82,6 +90,11 @@ struct Symbolic {
 // present in every row. `slot` = position in that CSR = Jacobian block slot.
 void analyze(int m, const std::vector<int64_t>& rowptr, const std::vector<int>& colidx, const SymbolicOptions& opt,
              Symbolic& out);
+
+#ifndef __CUDACC__
+constexpr int ING_NONE = INT32_MIN;    // (kernels.cuh defines the same pair for the device side)
+constexpr int ING_MULTI = 1 << 30;
+#endif
 
 // shared-memory bytes a panel needs in the factor kernel
 inline int panel_smem_bytes(int w, int h) { return ((w * (w + h) + h * w) * 4 + 6 * w + 10) * 8; }

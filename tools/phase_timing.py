@@ -15,18 +15,18 @@ optr, obr = eng.pack_outages([[k] for k in range(nscen)])
 eng.stage_outages(optr, obr)
 eng.run_staged()
 lib = L.load()
-buf0 = (C.c_double * 40)()
+buf0 = (C.c_double * 50)()
 lib.sblx_debug_phase_cycles.argtypes = [C.POINTER(C.c_double)]
 lib.sblx_debug_phase_cycles(buf0)
 eng.run_staged()
-buf1 = (C.c_double * 40)()
+buf1 = (C.c_double * 50)()
 lib.sblx_debug_phase_cycles(buf1)
 st = eng.stats()
-d = (np.array(buf1[:]) - np.array(buf0[:])).reshape(5, 8)
-names = ["ingest", "chain(w0)", "wait tasks", "U store", "schur(t0)", "cv", "tail"]
+d = (np.array(buf1[:]) - np.array(buf0[:])).reshape(5, 10)
+names = ["ingest", "chain(w0)", "wait ingest", "subst", "U store", "schur(t0)", "cv", "tail"]
 print("factor_ms", st["factor_ms"], "scenario_iterations", st["scenario_iterations"])
 tot = d.sum()
 for c, nt in enumerate([32, 64, 128, 256, 512]):
     row = d[c]
-    n = max(row[7], 1)
-    print("NT=%3d  CTAs %8d  avg cycles/CTA %8.0f | " % (nt, row[7], row[:7].sum() / n) + "  ".join("%s %6.0f" % (names[k], row[k] / n) for k in range(7)))
+    n = max(row[9], 1)
+    print("NT=%3d  CTAs %8d  avg cycles/CTA %8.0f | " % (nt, row[9], row[:8].sum() / n) + "  ".join("%s %6.0f" % (names[k], row[k] / n) for k in range(8)))
