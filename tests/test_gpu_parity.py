@@ -356,3 +356,46 @@ def test_full_size_10k_grid_parity_and_properties():
             keep = np.repeat(~iso[ns], 2)
             F = F[keep]
         assert np.max(np.abs(F)) <= 1e-8
+
+
+def test_full_size_10k_injection_sweep_parity():
+    """BASELINE config 4 shape: 100x100 tiled grid, load/injection sweep with independent truncated-normal factors
+    per load bus (f ~ N(1, 0.1) clipped to [0.5, 1.5], examples/powerflow/mc_probabilistic_powerflow.jl:28-41),
+    warm start from the base solution, Q-limit switching active.  Two scenarios are compared with the oracle in full;
+    every sampled scenario must satisfy the canonical mismatch at the returned V and keep switched buses at a limit."""
+    g = G.tiled_grid(rows=100, cols=100, augment=True, rating_mva=100.0)
+    a0 = M.build_arrays(g)
+    eng = api.Engine(a0)
+    Vb, conv, *_ = eng.solve_one(None)
+    assert conv
+    vm, va = np.abs(Vb), np.degrees(np.angle(Vb))
+    a = M.build_arrays(g, vm=vm, va_deg=va)
+    eng.set_v0(a.v0)
+    rng = np.random.default_rng(20260724)
+    B = 96
+    f = np.clip(rng.normal(1.0, 0.1, size=(B, g.n)), 0.5, 1.5)
+    isload = a.s_spec.real < 0
+    S = np.where(isload, a.s_spec * f, a.s_spec)
+    ql = np.where(isload, a.qload * f, a.qload)
+    raw = eng.solve_injections(S, ql)
+    eng.close()
+    assert raw["converged"].all()
+    assert raw["n_switch_events"].sum() > 0                   # the sweep does exercise PV -> PQ
+    for s in (0, 57):
+        o = O.runpf(g, vm, va, (), s_override=S[s], qload_override=ql[s])
+        assert o.converged and int(raw["iterations"][s]) == o.iters
+        assert np.max(np.abs(raw["V"][s] - o.V)) <= VTOL
+        assert np.array_equal(raw["bus_type_final"][s], o.types.astype(np.uint8))
+    Y = O.create_ybus(g, ())
+    vset = O.voltage_setpoints(g, vm)
+    qmin, qmax = O.q_limits_pu(g)
+    for s in range(0, B, 12):
+        t = raw["bus_type_final"][s].astype(np.int64)
+        Sc = O.calc_injections(Y, raw["V"][s])
+        sw = (a.bus_type == M.BUS_PV) & (t == M.BUS_PQ)
+        Sx = S[s].copy()
+        Sx[sw] = Sx[sw].real + 1j * Sc[sw].imag
+        F = O.mismatch_rectangular_fast(Y, raw["V"][s], Sx, t, vset, a.slack)
+        assert np.max(np.abs(F)) <= 1e-8
+        qg = Sc.imag + ql[s]
+        assert np.all((qg[sw] >= qmax[sw] - 1e-6) | (qg[sw] <= qmin[sw] + 1e-6))
