@@ -535,7 +535,7 @@ static void upload_model(sblx_handle* h) {
         g.wmax = std::max(g.wmax, P.w);
       }
       h->front_groups[l].push_back(g);
-      LaunchGroup gs{g.off, g.cnt, hs <= 32 ? 32 : hs <= 96 ? 64 : 128, hs * 16 + 64};
+      LaunchGroup gs{g.off, g.cnt, hs <= 32 ? 32 : hs <= 96 ? 64 : 128, hs * 16 + 64 + g.wmax * g.wmax * 32};
       h->solve_groups[l].push_back(gs);
       i = j;
     }

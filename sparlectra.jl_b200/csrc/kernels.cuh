@@ -1268,6 +1268,13 @@ __global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, 
   const double2* y = A.yv + (size_t)slot * M.m + P.first;
   const int* sn = M.struct_nodes + P.struct_ptr;
   for (int b = tid; b < h; b += NT) xs[b] = xv[sn[b]];
+  // the strictly upper part of the pivot block goes to shared memory now: the serial back substitution below must
+  // not pay one HBM round trip per pivot
+  double2* Ub = t + w;      // [w*w][2]
+  for (int idx = tid; idx < w * w; idx += NT) {
+    const int i = idx / w, j = idx - i * w;
+    if (j > i) { Ub[2 * idx] = U[2 * (i * nf + j)]; Ub[2 * idx + 1] = U[2 * (i * nf + j) + 1]; }
+  }
   __syncthreads();
   for (int p = warp; p < w; p += NT / 32) {
     double ax = 0.0, ay = 0.0;
@@ -1289,7 +1296,7 @@ __global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, 
     for (int p = w - 1; p >= 0; --p) {
       double ax = 0.0, ay = 0.0;
       if (lane > p && lane < w) {
-        const double2 u0 = U[2 * (p * nf + lane)], u1 = U[2 * (p * nf + lane) + 1];
+        const double2 u0 = Ub[2 * (p * w + lane)], u1 = Ub[2 * (p * w + lane) + 1];
         ax = u0.x * xc.x + u0.y * xc.y;
         ay = u1.x * xc.x + u1.y * xc.y;
       }
