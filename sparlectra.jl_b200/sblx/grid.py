@@ -439,3 +439,53 @@ def twin_lines() -> Grid:
     gb.add_pi_line("A", "B", 0.01, 0.08, 0.0)
     gb.add_pi_line("A", "B", 0.02, 0.16, 0.0)
     return gb.build()
+
+
+def random_meshed_grid(n=300, seed=1, extra_edge_frac=0.35, trafo_frac=0.12, shifter_frac=0.04, pv_frac=0.12,
+                       load_mw=(2.0, 12.0), pv_q_mvar=60.0, rating_mva=250.0) -> Grid:
+    """Irregular transmission-like test grid (NOT a reference generator): a random spanning tree plus
+    `extra_edge_frac * n` chords (average degree about 2.7 like the PEGASE cases), a share of the branches being
+    transformers with off-nominal ratio and a few phase shifters (Y12 != Y21, src/branch.jl:297-310), line
+    charging, bus shunts, loads on 70 % of the buses and regulating generators with finite Q limits.  Exercises
+    the minimum-degree / nested-dissection symbolic code and the asymmetric stamps on a non-mesh topology."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    gb = GridBuilder(f"rand{n}_{seed}", 100.0)
+    for i in range(n):
+        gb.add_bus(f"N{i + 1}", vm_pu=1.0, va_deg=0.0)
+    edges = set()
+    for i in range(1, n):                       # random recursive tree with short-range attachment
+        j = int(rng.integers(max(0, i - 12), i))
+        edges.add((j, i))
+    target = n - 1 + int(extra_edge_frac * n)
+    while len(edges) < target:
+        i = int(rng.integers(0, n))
+        j = int(np.clip(i + rng.integers(-25, 26), 0, n - 1))
+        if i != j and (min(i, j), max(i, j)) not in edges:
+            edges.add((min(i, j), max(i, j)))
+    for (i, j) in sorted(edges):
+        x = float(rng.uniform(0.01, 0.08))
+        r = x * float(rng.uniform(0.1, 0.4))
+        u = rng.random()
+        if u < shifter_frac:
+            gb.add_pi_line(i, j, 0.1 * r, x, 0.0, 0.0, rating=rating_mva, ratio=float(rng.uniform(0.97, 1.03)),
+                           shift_deg=float(rng.uniform(-3.0, 3.0)))
+        elif u < shifter_frac + trafo_frac:
+            gb.add_pi_line(i, j, 0.1 * r, x, 0.0, 0.0, rating=rating_mva, ratio=float(rng.uniform(0.94, 1.06)))
+        else:
+            gb.add_pi_line(i, j, r, x, float(rng.uniform(0.0, 0.04)), 0.0, rating=rating_mva)
+    loads = rng.random(n) < 0.7
+    total = 0.0
+    for i in range(1, n):
+        if loads[i]:
+            p = float(rng.uniform(*load_mw))
+            gb.add_prosumer(i, "ENERGYCONSUMER", p=p, q=0.3 * p)
+            total += p
+        if rng.random() < 0.05:
+            gb.add_shunt(i, 0.0, float(rng.uniform(2.0, 8.0)))
+    pv = [i for i in range(1, n) if rng.random() < pv_frac]
+    share = 0.9 * total / max(1, len(pv))
+    for i in pv:
+        gb.add_prosumer(i, "GENERATOR", p=share, q=0.0, vm_pu=float(rng.choice([1.0, 1.01, 1.02])), qMin=-pv_q_mvar,
+                        qMax=pv_q_mvar)
+    gb.add_prosumer(0, "EXTERNALNETWORKINJECTION", p=0.0, q=0.0, vm_pu=1.02, va_deg=0.0, reference=True)
+    return gb.build()

@@ -399,3 +399,19 @@ def test_full_size_10k_injection_sweep_parity():
         assert np.max(np.abs(F)) <= 1e-8
         qg = Sc.imag + ql[s]
         assert np.all((qg[sw] >= qmax[sw] - 1e-6) | (qg[sw] <= qmin[sw] + 1e-6))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_irregular_grid_with_transformers_and_phase_shifters_n1_parity(seed):
+    """Non-mesh topology (random tree + chords, average degree 2.7) with off-nominal transformers, phase shifters
+    (Y12 != Y21), line charging and bus shunts: full N-1 (radial branches split the grid -> island handling) plus
+    random N-2, every scenario compared with the oracle."""
+    g = G.random_meshed_grid(300, seed)
+    n1 = O.generate_n1_branches(g)
+    rng = np.random.default_rng(100 + seed)
+    n2 = [sorted(rng.choice(g.nbranch, size=2, replace=False).tolist()) for _ in range(60)]
+    cases = n1 + n2
+    raw, oracle, _ = _run_both(g, cases)
+    _compare_batch(g, cases, raw, oracle, f"rand300_{seed}")
+    assert raw["n_switch_events"].sum() > 0
+    assert (raw["island_count"] > 1).any()              # radial spurs: some outages island part of the grid

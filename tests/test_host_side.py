@@ -202,3 +202,13 @@ def test_matpower_reader_text_rules():
         MP.read_case_m("mpc.bus = [1 2 3];\n")
     with pytest.raises(ValueError, match="mpc.gen"):
         MP.read_case_m("mpc.baseMVA = 100;\nmpc.bus = [1 3 0 0 0 0 1 1 0 1 1 1 1];\n")
+
+
+@pytest.mark.parametrize("n,seed", [(300, 1), (1500, 7)])
+def test_symbolic_selftest_on_irregular_grids(n, seed):
+    g = G.random_meshed_grid(n, seed)
+    a = M.build_arrays(g)
+    for ordering in (1, 2):
+        info, res = api.analyze_only(a.Y, a.slack, ordering=ordering)
+        assert res < 1e-10, (ordering, res)
+        assert info["nnz_lu_scalar"] >= info["nnz_j_scalar"]
