@@ -166,7 +166,8 @@ static void build_nodes_and_symbolic(HostModel& H, const sblx_options& o) {
   so.relax_zero_frac = o.relax_zero_frac;
   if (o.relax_small > 0) so.relax_small = o.relax_small;
   if (o.panel_smem_kb >= 4.0 && o.panel_smem_kb <= 200.0) so.smem_budget_bytes = (int)(o.panel_smem_kb * 1024);
-  if (const char* e = getenv("SBLX_ND_LEAF")) so.nd_leaf = std::max(4, atoi(e));   // tuning probe
+  if (const char* e = getenv("SBLX_ND_LEAF")) so.nd_leaf = std::max(4, atoi(e));   // tuning probes
+  if (const char* e = getenv("SBLX_RELAX_MAXW")) so.relax_small_max_w = atoi(e);
   analyze(H.m, H.jb_rowptr, H.jb_col, so, H.sym);
   if (H.sym.max_w > 16) throw std::runtime_error("sblx: panel wider than 16 pivots");
 }
@@ -536,6 +537,7 @@ static void upload_model(sblx_handle* h) {
       }
       h->front_groups[l].push_back(g);
       LaunchGroup gs{g.off, g.cnt, hs <= 32 ? 32 : hs <= 96 ? 64 : 128, hs * 16 + 64 + g.wmax * g.wmax * 32};
+      gs.lanes = g.lanes < 32 ? 8 : gs.nt;      // the lane-group front classes have pivot blocks of <= 8 buses
       h->solve_groups[l].push_back(gs);
       i = j;
     }
@@ -958,6 +960,17 @@ static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
   dim3 grid(nstep, g.cnt);
   k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
 }
+static void launch_solve_group(sblx_handle* h, const LaunchGroup& g, int nstep) {
+  if (g.lanes == 8) {
+    k_backsolve_small<<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+    return;
+  }
+  switch (g.nt) {
+    case 32: launch_solve<32>(h, g, nstep); break;
+    case 64: launch_solve<64>(h, g, nstep); break;
+    default: launch_solve<128>(h, g, nstep); break;
+  }
+}
 
 // numeric factorisation of the step set: level by level
 static void launch_factor(sblx_handle* h, int nstep) {
@@ -1084,11 +1097,7 @@ static void run_staged(sblx_handle* h) {
     if (nstep > 0) {
       for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
         for (const LaunchGroup& g : h->solve_groups[l]) {
-          switch (g.nt) {
-            case 32: launch_solve<32>(h, g, nstep); break;
-            case 64: launch_solve<64>(h, g, nstep); break;
-            default: launch_solve<128>(h, g, nstep); break;
-          }
+          launch_solve_group(h, g, nstep);
           st.launches++;
         }
     }
@@ -1578,11 +1587,7 @@ int sblx_debug_newton_step(sblx_handle* h, int64_t nout, const int32_t* outage_b
   launch_factor(h, 1);
   for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
     for (const LaunchGroup& g : h->solve_groups[l]) {
-      switch (g.nt) {
-        case 32: launch_solve<32>(h, g, 1); break;
-        case 64: launch_solve<64>(h, g, 1); break;
-        default: launch_solve<128>(h, g, 1); break;
-      }
+      launch_solve_group(h, g, 1);
     }
   CK(cudaGetLastError());
   std::vector<double2> rhs(m), xv(m);

@@ -1311,6 +1311,51 @@ __global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, 
   }
 }
 
+// Back substitution for the tiny fronts (pivot blocks of <= 8 buses, the lane-group classes of k_front): 8 lanes
+// per scenario, 4 scenarios per one-warp CTA.  Lane p owns pivot row p: it walks its U' row sequentially (one
+// 256-bit load per block, no shuffle reductions), then the w x w triangle is resolved with one broadcast per pivot.
+__global__ void __launch_bounds__(32) k_backsolve_small(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+  constexpr int G = 8, NG = 32 / G;
+  const int nact = L.counts[2];
+  if ((int)blockIdx.x * NG >= nact) return;
+  const int bscen = min((int)blockIdx.x * NG + (int)threadIdx.x / G, nact - 1);   // past the end: repeat the last one
+  const int slot = L.step[bscen];
+  const PanelDev P = M.panels[panel_ids[blockIdx.y]];
+  const int w = P.w, h = P.h, nf = w + h;
+  const int p = threadIdx.x % G;
+  double2* xv = A.xv + (size_t)slot * M.m;
+  const double2* U = reinterpret_cast<const double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
+  const int* sn = M.struct_nodes + P.struct_ptr;
+  double2 r = make_double2(0.0, 0.0);
+  double2 tu0[G], tu1[G];                        // this row's part of the pivot block (columns right of the diagonal)
+#pragma unroll
+  for (int j = 0; j < G; ++j) { tu0[j] = make_double2(0.0, 0.0); tu1[j] = tu0[j]; }
+  if (p < w) {
+    r = A.yv[(size_t)slot * M.m + P.first + p];
+#pragma unroll
+    for (int j = 1; j < G; ++j)
+      if (j > p && j < w) ldg_blk(U + 2 * (p * nf + j), tu0[j], tu1[j]);
+    const double2* row = U + 2 * (size_t)(p * nf + w);
+    for (int b = 0; b < h; ++b) {
+      double2 u0, u1;
+      ldg_blk(row + 2 * b, u0, u1);
+      const double2 x = xv[sn[b]];
+      r.x -= u0.x * x.x + u0.y * x.y;
+      r.y -= u1.x * x.x + u1.y * x.y;
+    }
+  }
+#pragma unroll
+  for (int j = G - 1; j >= 1; --j) {
+    // lane j's r is final once every column right of it has been applied
+    const double xjx = __shfl_sync(0xffffffffu, r.x, j, G), xjy = __shfl_sync(0xffffffffu, r.y, j, G);
+    if (j < w && p < j) {
+      r.x -= tu0[j].x * xjx + tu0[j].y * xjy;
+      r.y -= tu1[j].x * xjx + tu1[j].y * xjy;
+    }
+  }
+  if (p < w) xv[P.first + p] = r;
+}
+
 // V += damp * dx (slack untouched).  grid (ceil(m/8), ceil(nStep/32)), block (32, 8)
 __global__ void __launch_bounds__(256) k_update(DevModel M, Slots A, Lists L) {
   const int ns = L.counts[2];

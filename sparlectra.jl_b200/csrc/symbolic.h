@@ -20,6 +20,7 @@ struct SymbolicOptions {
   int smem_budget_bytes = 200 * 1024;  // panel budget per front (dynamic shared memory)
   int max_panel_width = 16;    // cap on pivots per panel (the pivot block is factored in one warp's registers: 32 scalar columns)
   int relax_small = 12;        // always merge a child when the merged front has <= this many nodes
+  int relax_small_max_w = 4;   // ... as long as the merged pivot block stays within the small-front kernels' width
   double relax_zero_frac = 0.25;  // else merge when introduced explicit zeros <= frac * merged front area
   int nd_leaf = 48;            // nested dissection stops at subgraphs of this many nodes (ordered by MD)
 };

@@ -442,7 +442,7 @@ def twin_lines() -> Grid:
 
 
 def random_meshed_grid(n=300, seed=1, extra_edge_frac=0.35, trafo_frac=0.12, shifter_frac=0.04, pv_frac=0.12,
-                       load_mw=(2.0, 12.0), pv_q_mvar=60.0, rating_mva=250.0) -> Grid:
+                       load_mw=(2.0, 12.0), pv_q_mvar=60.0, rating_mva=250.0, gen_share=0.9) -> Grid:
     """Irregular transmission-like test grid (NOT a reference generator): a random spanning tree plus
     `extra_edge_frac * n` chords (average degree about 2.7 like the PEGASE cases), a share of the branches being
     transformers with off-nominal ratio and a few phase shifters (Y12 != Y21, src/branch.jl:297-310), line
@@ -483,7 +483,7 @@ def random_meshed_grid(n=300, seed=1, extra_edge_frac=0.35, trafo_frac=0.12, shi
         if rng.random() < 0.05:
             gb.add_shunt(i, 0.0, float(rng.uniform(2.0, 8.0)))
     pv = [i for i in range(1, n) if rng.random() < pv_frac]
-    share = 0.9 * total / max(1, len(pv))
+    share = gen_share * total / max(1, len(pv))   # large n: use ~1.01 (the slack sits at one end of a long chain)
     for i in pv:
         gb.add_prosumer(i, "GENERATOR", p=share, q=0.0, vm_pu=float(rng.choice([1.0, 1.01, 1.02])), qMin=-pv_q_mvar,
                         qMax=pv_q_mvar)
