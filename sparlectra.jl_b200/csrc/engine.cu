@@ -363,7 +363,7 @@ struct sblx_handle {
   DevBuf<double> d_vset, d_qmin, d_qmax, d_qload, d_rating;
   DevBuf<unsigned char> d_type0, d_lock, d_br_status;
   DevBuf<int> d_br_from, d_br_to;
-  DevBuf<PanelDev> d_panels;
+  DevBuf<PanelDev> d_panels, d_panels_lv;     // by panel id / in level_panels order (contiguous per launch group)
   DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels, d_ing_ptr, d_ing_src, d_ing_pairs, d_ing_xptr, d_ing_xsrc, d_vec_ptr, d_vec_src;
   DevBuf<ChildDev> d_childdev;
   DevBuf<long long> d_rel_ptr, d_inv_ptr;
@@ -547,6 +547,11 @@ static void upload_model(sblx_handle* h) {
     lp.insert(lp.end(), ids.begin(), ids.end());
   }
   h->d_level_panels.upload(lp, s);
+  {
+    std::vector<PanelDev> plv(lp.size());
+    for (size_t i = 0; i < lp.size(); ++i) plv[i] = pd[lp[i]];
+    h->d_panels_lv.upload(plv, s);
+  }
   CK(cudaStreamSynchronize(s));
   // opt-in shared memory
   CK(cudaFuncSetAttribute(k_front<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
@@ -953,16 +958,16 @@ static void launch_front(sblx_handle* h, const LaunchGroup& g, int nstep) {
   constexpr int NG = NT / G;                       // scenarios per CTA
   const int stride = (g.smem + 15) / 16;           // double2 per scenario group
   dim3 grid((nstep + NG - 1) / NG, g.cnt);
-  k_front<NT, G><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off, stride);
+  k_front<NT, G><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off, stride);
 }
 template <int NT>
 static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
   dim3 grid(nstep, g.cnt);
-  k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+  k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off);
 }
 static void launch_solve_group(sblx_handle* h, const LaunchGroup& g, int nstep) {
   if (g.lanes == 8) {
-    k_backsolve_small<<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->L, h->d_level_panels.p + g.off);
+    k_backsolve_small<<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off);
     return;
   }
   switch (g.nt) {

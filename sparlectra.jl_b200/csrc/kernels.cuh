@@ -565,7 +565,7 @@ template <int NT, int G = NT>
 #define SBLX_OCC128 3
 #endif
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? SBLX_OCC128 : NT == 64 ? 10 : NT == 32 ? (G < 32 ? 8 : 16) : 1))
-k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int group_stride) {
+k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels, int group_stride) {
   static_assert(G == NT || NT == 32, "lane groups need a one-warp CTA");
   extern __shared__ double2 sm2_all[];
   constexpr int NG = NT / G;
@@ -573,9 +573,8 @@ k_front(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids, int gro
   if ((int)blockIdx.x * NG >= nact) return;
   // a group past the end repeats the last scenario (identical values to identical addresses): no predication needed
   const int bscen = min((int)blockIdx.x * NG + (int)threadIdx.x / G, nact - 1);
-  const int panel = panel_ids[blockIdx.y];
   const int slot = L.step[bscen];
-  const PanelDev P = M.panels[panel];
+  const PanelDev P = group_panels[blockIdx.y];          // the launch group's panel records, contiguous: no id indirection
   const int w = P.w, h = P.h, nf = w + h;
   const int tid = G == NT ? (int)threadIdx.x : (int)threadIdx.x % G;    // thread index within the scenario's group
   double2* sm2 = sm2_all + (G == NT ? 0 : ((int)threadIdx.x / G) * group_stride);
@@ -1253,12 +1252,11 @@ __global__ void __launch_bounds__(128, 4) k_schur(DevModel M, Slots A, Lists L, 
 // K4: back substitution of one front: x_P = y' - U'_PP x_P(upper) - U'_PR x_R.  w <= 32.
 // ------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+__global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels) {
   extern __shared__ double2 sm2[];
-  const int panel = panel_ids[blockIdx.y];              // grid: x = scenario (fastest), y = front
-  if ((int)blockIdx.x >= L.counts[2]) return;
+  if ((int)blockIdx.x >= L.counts[2]) return;          // grid: x = scenario (fastest), y = front
   const int slot = L.step[blockIdx.x];
-  const PanelDev P = M.panels[panel];
+  const PanelDev P = group_panels[blockIdx.y];
   const int w = P.w, h = P.h, nf = w + h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* xs = sm2;        // [h]
@@ -1314,13 +1312,13 @@ __global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, 
 // Back substitution for the tiny fronts (pivot blocks of <= 8 buses, the lane-group classes of k_front): 8 lanes
 // per scenario, 4 scenarios per one-warp CTA.  Lane p owns pivot row p: it walks its U' row sequentially (one
 // 256-bit load per block, no shuffle reductions), then the w x w triangle is resolved with one broadcast per pivot.
-__global__ void __launch_bounds__(32) k_backsolve_small(DevModel M, Slots A, Lists L, const int* __restrict__ panel_ids) {
+__global__ void __launch_bounds__(32) k_backsolve_small(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels) {
   constexpr int G = 8, NG = 32 / G;
   const int nact = L.counts[2];
   if ((int)blockIdx.x * NG >= nact) return;
   const int bscen = min((int)blockIdx.x * NG + (int)threadIdx.x / G, nact - 1);   // past the end: repeat the last one
   const int slot = L.step[bscen];
-  const PanelDev P = M.panels[panel_ids[blockIdx.y]];
+  const PanelDev P = group_panels[blockIdx.y];
   const int w = P.w, h = P.h, nf = w + h;
   const int p = threadIdx.x % G;
   double2* xv = A.xv + (size_t)slot * M.m;
