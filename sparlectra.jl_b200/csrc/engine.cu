@@ -334,6 +334,7 @@ struct LaunchGroup {
   int off, cnt, nt, smem;     // range in d_level_panels, threads, dynamic smem bytes
   int subst_chunks = 0, schur_tiles = 0, wmax = 0;   // split path: grid.z of k_subst / k_schur, widest panel
   int lanes = 0;              // k_front: lanes per scenario (< nt: several scenarios share one warp)
+  int wide = 0;               // k_front<64>: pivot blocks of 9..16 buses
 };
 
 struct HostResults {
@@ -504,10 +505,11 @@ static void upload_model(sblx_handle* h) {
     if (P.w <= 4 && bytes <= g8_bytes) return 0;
     if (P.w <= 8 && bytes <= g16_bytes) return 1;
     int c = front_class_b(bytes);
-    return 2 + ((P.w > 8 && c < 2) ? 2 : c);
+    return (P.w > 8 && c < 2) ? 7 : 2 + c;          // 7: small front with a wide pivot block (64 threads, 16-row register column)
   };
-  static const int front_nt[7] = {32, 32, 32, 64, 128, 256, 512};
-  static const int front_g[7] = {8, 16, 32, 64, 128, 256, 512};
+  static const int front_nt[8] = {32, 32, 32, 64, 128, 256, 512, 64};
+  static const int front_g[8] = {8, 16, 32, 64, 128, 256, 512, 64};
+  static const int front_wide[8] = {0, 0, 0, 0, 0, 0, 0, 1};
   std::vector<int> lp;
   h->front_groups.assign(S.nlevels, {});
   h->solve_groups.assign(S.nlevels, {});
@@ -528,6 +530,7 @@ static void upload_model(sblx_handle* h) {
       }
       LaunchGroup g{(int)lp.size() + (int)i, (int)(j - i), front_nt[c], smem};
       g.lanes = front_g[c];
+      g.wide = front_wide[c];
       for (size_t q = i; q < j; ++q) {
         const Panel& P = S.panels[ids[q]];
         const int hpad = (P.h + 31) & ~31;
@@ -558,6 +561,7 @@ static void upload_model(sblx_handle* h) {
   CK(cudaFuncSetAttribute(k_front<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
   CK(cudaFuncSetAttribute(k_front<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024));
   CK(cudaFuncSetAttribute(k_front<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+  CK(cudaFuncSetAttribute(k_front<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
   CK(cudaFuncSetAttribute(k_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   CK(cudaFuncSetAttribute(k_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   CK(cudaFuncSetAttribute(k_front<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -953,12 +957,12 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   h->ran = false;
 }
 
-template <int NT, int G = NT>
+template <int NT, int G = NT, bool WIDE = false>
 static void launch_front(sblx_handle* h, const LaunchGroup& g, int nstep) {
   constexpr int NG = NT / G;                       // scenarios per CTA
   const int stride = (g.smem + 15) / 16;           // double2 per scenario group
   dim3 grid((nstep + NG - 1) / NG, g.cnt);
-  k_front<NT, G><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off, stride);
+  k_front<NT, G, WIDE><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off, stride);
 }
 template <int NT>
 static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
@@ -990,7 +994,10 @@ static void launch_factor(sblx_handle* h, int nstep) {
             else if (g.lanes == 16) launch_front<32, 16>(h, g, nstep);
             else launch_front<32>(h, g, nstep);
             break;
-          case 64: launch_front<64>(h, g, nstep); break;
+          case 64:
+            if (g.wide) launch_front<64, 64, true>(h, g, nstep);
+            else launch_front<64>(h, g, nstep);
+            break;
           case 128: launch_front<128>(h, g, nstep); break;
           case 256: launch_front<256>(h, g, nstep); break;
           default: launch_front<512>(h, g, nstep); break;

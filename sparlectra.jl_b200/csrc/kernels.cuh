@@ -557,14 +557,16 @@ __device__ __forceinline__ void bmsub(double2& t0, double2& t1, double2 a0, doub
 // the warp is split into NT/G lane groups, each factoring the same small front of a DIFFERENT scenario in its own
 // slice of shared memory - tiny fronts (w <= G/2 pivots) leave most of a warp idle otherwise, and the per-front
 // instruction overhead is shared by the groups.
-template <int NT, int G = NT>
+// WIDE (64-thread class only): 16-row register column, for the few small fronts whose pivot block is wider than 8
+// buses (dense root fronts of a minimum-degree tree) - they would otherwise fall into the 128-thread class.
+template <int NT, int G = NT, bool WIDE = false>
 #ifndef SBLX_INGEST_BATCH
 #define SBLX_INGEST_BATCH 2
 #endif
 #ifndef SBLX_OCC128
 #define SBLX_OCC128 3
 #endif
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? SBLX_OCC128 : NT == 64 ? 10 : NT == 32 ? (G < 32 ? 8 : 16) : 1))
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? SBLX_OCC128 : NT == 64 ? (WIDE ? 6 : 10) : NT == 32 ? (G < 32 ? 8 : 16) : 1))
 k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels, int group_stride) {
   static_assert(G == NT || NT == 32, "lane groups need a one-warp CTA");
   extern __shared__ double2 sm2_all[];
@@ -661,7 +663,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
     const int lane = tid;                        // lane within the scenario's group: shuffles below use width G
     const int bc = lane >> 1, hi = lane & 1;
     constexpr int SW = G < 32 ? G : 32;          // shuffle width
-    constexpr int WR = G < 32 ? G / 2 : (NT <= 64) ? 8 : 16;   // register column (host class rule: w <= WR)
+    constexpr int WR = G < 32 ? G / 2 : (NT <= 64 && !WIDE) ? 8 : 16;   // register column (host class rule: w <= WR)
     double a[2 * WR];
 #pragma unroll
     for (int bi = 0; bi < WR; ++bi) {
