@@ -490,9 +490,11 @@ static void upload_model(sblx_handle* h) {
   h->d_inv_ptr.upload(ip, s);
   // launch groups: per level, panels sorted by size class
   // size class by panel bytes; the two small classes factor the pivot block with an 8-pivot register column
-  // Classes 0/1 are the lane-group kernels (8 / 16 lanes per scenario: pivot blocks of <= 4 / <= 8 buses, 4 / 2
-  // scenarios per warp); classes 2..6 give the whole CTA (32..512 threads) to one front.
-  int g8_bytes = 4 * 1024, g16_bytes = 8 * 1024;
+  // Classes 8/0/1 are the lane-group kernels (4 / 8 / 16 lanes per scenario: pivot blocks of <= 2 / <= 4 / <= 8
+  // buses, 8 / 4 / 2 scenarios per warp); classes 2..6 give the whole CTA (32..512 threads) to one front; class 7
+  // is the 64-thread kernel with a 16-row register column (small fronts with pivot blocks of 9..16 buses).
+  int g8_bytes = 4 * 1024, g16_bytes = 8 * 1024, g4_bytes = 1024;
+  if (const char* e = getenv("SBLX_G4_KB10")) g4_bytes = atoi(e) * 102;        // tuning probe, tenths of a KB (0 disables the class)
   if (const char* e = getenv("SBLX_G8_KB")) g8_bytes = atoi(e) * 1024;       // tuning probes (0 disables the class)
   if (const char* e = getenv("SBLX_G16_KB")) g16_bytes = atoi(e) * 1024;
   g8_bytes = std::min(g8_bytes, 12 * 1024);
@@ -502,14 +504,15 @@ static void upload_model(sblx_handle* h) {
   auto front_class_b = [c2_bytes](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= c2_bytes ? 2 : bytes <= 110 * 1024 ? 3 : 4; };
   auto front_class_p = [&](const Panel& P) {
     const int bytes = panel_smem_bytes(P.w, P.h);
+    if (P.w <= 2 && bytes <= g4_bytes) return 8;      // 4 lanes per scenario, 8 scenarios per warp
     if (P.w <= 4 && bytes <= g8_bytes) return 0;
     if (P.w <= 8 && bytes <= g16_bytes) return 1;
     int c = front_class_b(bytes);
     return (P.w > 8 && c < 2) ? 7 : 2 + c;          // 7: small front with a wide pivot block (64 threads, 16-row register column)
   };
-  static const int front_nt[8] = {32, 32, 32, 64, 128, 256, 512, 64};
-  static const int front_g[8] = {8, 16, 32, 64, 128, 256, 512, 64};
-  static const int front_wide[8] = {0, 0, 0, 0, 0, 0, 0, 1};
+  static const int front_nt[9] = {32, 32, 32, 64, 128, 256, 512, 64, 32};
+  static const int front_g[9] = {8, 16, 32, 64, 128, 256, 512, 64, 4};
+  static const int front_wide[9] = {0, 0, 0, 0, 0, 0, 0, 1, 0};
   std::vector<int> lp;
   h->front_groups.assign(S.nlevels, {});
   h->solve_groups.assign(S.nlevels, {});
@@ -557,6 +560,7 @@ static void upload_model(sblx_handle* h) {
   }
   CK(cudaStreamSynchronize(s));
   // opt-in shared memory
+  CK(cudaFuncSetAttribute(k_front<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
   CK(cudaFuncSetAttribute(k_front<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
   CK(cudaFuncSetAttribute(k_front<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
   CK(cudaFuncSetAttribute(k_front<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024));
@@ -990,7 +994,8 @@ static void launch_factor(sblx_handle* h, int nstep) {
       for (const LaunchGroup& g : h->front_groups[l]) {
         switch (g.nt) {
           case 32:
-            if (g.lanes == 8) launch_front<32, 8>(h, g, nstep);
+            if (g.lanes == 4) launch_front<32, 4>(h, g, nstep);
+            else if (g.lanes == 8) launch_front<32, 8>(h, g, nstep);
             else if (g.lanes == 16) launch_front<32, 16>(h, g, nstep);
             else launch_front<32>(h, g, nstep);
             break;
