@@ -83,8 +83,10 @@ typedef struct sblx_options {
   int32_t freeze_after_repeated_switching; /* [1] */
   int32_t device;               /* CUDA device ordinal, -1 = current [-1] */
   int32_t max_slots;            /* scenario slots resident on the GPU, 0 = auto from free memory [0] */
-  int32_t ordering;             /* 0 auto, 1 minimum degree, 2 nested dissection [0] */
-  int32_t relax_small;          /* always merge a child front when the merged front has <= this many buses [18] */
+  int32_t ordering;             /* 0 auto (cheaper of the two by fill + a per-level launch charge), 1 minimum degree,
+                                   2 nested dissection [0] */
+  int32_t relax_small;          /* merge a child front when the merged front has <= this many buses and its pivot
+                                   block stays <= 4 buses (the leanest kernel class) [18] */
   int32_t factor_mode;          /* 0 = one fused CTA per front (k_front, default), 1 = experimental split kernels per level
                                    (k_pivot / k_subst / k_schur; measured slower: profiles/README.md) [0] */
   int32_t reserved1;
