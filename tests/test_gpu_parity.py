@@ -415,3 +415,32 @@ def test_irregular_grid_with_transformers_and_phase_shifters_n1_parity(seed):
     _compare_batch(g, cases, raw, oracle, f"rand300_{seed}")
     assert raw["n_switch_events"].sum() > 0
     assert (raw["island_count"] > 1).any()              # radial spurs: some outages island part of the grid
+
+
+def test_randomised_grids_and_symbolic_options_parity():
+    """Random grid shapes x random symbolic options (ordering, amalgamation, panel budget: they select different
+    kernel classes and index-list paths), a handful of N-1 / N-2 scenarios each, every one against the oracle
+    (the long version is tools/stress.py)."""
+    rng = np.random.default_rng(20261020)
+    for r in range(8):
+        if r % 2 == 0:
+            g = G.tiled_grid(rows=int(rng.integers(4, 30)), cols=int(rng.integers(4, 30)), augment=True,
+                             pv_every=int(rng.integers(3, 8)), pv_q_mvar=float(rng.uniform(15, 40)))
+        else:
+            g = G.random_meshed_grid(int(rng.integers(40, 700)), int(rng.integers(1, 10**6)),
+                                     extra_edge_frac=float(rng.uniform(0.1, 0.8)), gen_share=float(rng.uniform(0.9, 1.0)))
+        opts = dict(ordering=int(rng.integers(0, 3)), relax_small=int(rng.integers(2, 40)),
+                    relax_zero_frac=float(rng.uniform(0.0, 0.4)), panel_smem_kb=float(rng.choice([24, 48, 100, 200])))
+        vm, va, flat, base = O.solve_base(g)
+        eng = api.Engine(M.build_arrays(g, vm=vm, va_deg=va, flatstart=flat), **opts)
+        cases = [[int(k)] for k in rng.choice(g.nbranch, size=min(10, g.nbranch), replace=False)] + \
+                [sorted(int(x) for x in rng.choice(g.nbranch, size=2, replace=False)) for _ in range(3)]
+        raw = eng.solve_outages(cases)
+        eng.close()
+        for i, c in enumerate(cases):
+            o = O.runpf(g, vm, va, c)
+            tag = (g.name, opts, c)
+            assert bool(raw["converged"][i]) == o.converged and int(raw["iterations"][i]) == o.iters, tag
+            if o.converged:
+                assert np.max(np.abs(raw["V"][i] - o.V)) <= VTOL, tag
+                assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8)), tag
