@@ -835,7 +835,8 @@ def solve_base(grid, maxiter=30, tol=1e-8, **kw):
     return grid.vm0.copy(), grid.va0_deg.copy(), True, r
 
 
-def run_contingencies(grid, cases, vm_min=0.9, vm_max=1.1, maxiter=30, tol=1e-8, keep_v=True, **kw):
+def run_contingencies(grid, cases, vm_min=0.9, vm_max=1.1, maxiter=30, tol=1e-8, keep_v=True,
+                      retry_flat_start=False, **kw):
     vm, va, flat, _ = solve_base(grid, maxiter, tol, **kw)
     out = []
     for ci, removed in enumerate(cases):
@@ -846,6 +847,11 @@ def run_contingencies(grid, cases, vm_min=0.9, vm_max=1.1, maxiter=30, tol=1e-8,
                                          "unknown branch", reason=R_UNKNOWN_BRANCH))
             continue
         r = runpf(grid, vm, va, removed, maxiter=maxiter, tol=tol, flatstart=flat, **kw)
+        if (not r.converged) and r.reason != R_ISLANDED_NO_REF and retry_flat_start:
+            # one bounded second attempt from a flat start, iterations summed (contingency.jl:195-207)
+            r2 = runpf(grid, vm, va, removed, maxiter=maxiter, tol=tol, flatstart=True, **kw)
+            r2.iters += r.iters
+            r = r2
         if r.reason == R_ISLANDED_NO_REF:
             out.append(ContingencyResult(name, False, r.iters, math.nan, math.nan, math.nan, [], [], r.island_count,
                                          "islanded without reference", V=r.V if keep_v else None, reason=r.reason,

@@ -201,7 +201,8 @@ const _STATUS_TEXT = Dict(7 => "islanded without reference", 8 => "unknown branc
                           9 => "islanded (island-wise solve not supported by the batched backend)")
 
 function runContingenciesBatched!(net::Sparlectra.Net, cases::Vector{Sparlectra.ContingencyCase};
-                                  vm_min_pu::Float64 = 0.9, vm_max_pu::Float64 = 1.1, maxIte::Int = 30, tol::Float64 = 1e-8, kwargs...)
+                                  vm_min_pu::Float64 = 0.9, vm_max_pu::Float64 = 1.1, maxIte::Int = 30, tol::Float64 = 1e-8,
+                                  retry_flat_start::Bool = false, kwargs...)
   vm_min_pu < vm_max_pu || throw(ArgumentError("runContingencies!: vm_min_pu must be below vm_max_pu."))
   isempty(cases) && return Sparlectra.ContingencyResult[]
   template = deepcopy(net)                                   # the caller's net is never mutated
@@ -217,6 +218,23 @@ function runContingenciesBatched!(net::Sparlectra.Net, cases::Vector{Sparlectra.
   eng = Engine(template; tol = tol, maxIte = maxIte, vm_min_pu = vm_min_pu, vm_max_pu = vm_max_pu, kwargs...)
   idx = [Sparlectra._resolve_contingency_branch(template, c.element) for c in cases]
   raw = solve_outages(eng, [i === nothing ? [0] : [i] for i in idx])
+  if retry_flat_start
+    # one second batch from a flat start for the cases that did not converge, iterations summed (contingency.jl:195-207)
+    again = [k for k in eachindex(cases) if idx[k] !== nothing && raw.converged[k] == 0 && 1 <= raw.status[k] <= 6]
+    if !isempty(again)
+      flat = deepcopy(template); flat.flatstart = true
+      eng2 = Engine(flat; tol = tol, maxIte = maxIte, vm_min_pu = vm_min_pu, vm_max_pu = vm_max_pu, kwargs...)
+      raw2 = solve_outages(eng2, [[idx[k]] for k in again])
+      for (j, k) in enumerate(again)
+        it1 = raw.iterations[k]
+        for f in (:converged, :status, :iterations, :n_switch_events, :island_count, :final_mismatch, :vmin_pu, :vmax_pu, :max_loading_pct)
+          getfield(raw, f)[k] = getfield(raw2, f)[j]
+        end
+        raw.V[:, k] .= view(raw2.V, :, j)
+        raw.iterations[k] += it1
+      end
+    end
+  end
   busnames = Dict{Int,String}(i => name for (name, i) in template.busDict)
   out = Vector{Sparlectra.ContingencyResult}(undef, length(cases))
   for (k, c) in enumerate(cases)

@@ -383,10 +383,11 @@ def _resolve_branch(grid, element: str):
 
 
 def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30, tol=1e-8, backend=None,
-                            return_raw=False, **kwargs):
+                            return_raw=False, retry_flat_start=False, **kwargs):
     """runContingencies! (src/contingency.jl:257-319) with the batched B200 backend: the
     base case is solved first (warm-start template; on failure the cases start flat), then
-    ALL cases go to the GPU in one call.  Results come back in input order."""
+    ALL cases go to the GPU in one call.  Results come back in input order.  `retry_flat_start`: the cases that did
+    not converge get one second batch from a flat start, iterations summed (contingency.jl:195-207)."""
     if not (vm_min_pu < vm_max_pu):
         raise ValueError("runContingencies!: vm_min_pu must be below vm_max_pu.")
     if len(cases) == 0:
@@ -411,6 +412,20 @@ def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30
         idx = [_resolve_branch(grid, c.element) for c in cases]
         lists = [[k] if k is not None else [-1] for k in idx]
         raw = eng.solve_outages(lists, want_v=True, want_types=return_raw)
+        if retry_flat_start:
+            again = [i for i in range(len(cases)) if idx[i] is not None and not raw["converged"][i] and 1 <= int(raw["status"][i]) <= 6]
+            if again:
+                eng.close()
+                vmt, vat = (np.abs(Vb), np.degrees(np.angle(Vb))) if conv else (None, None)
+                a3 = M.build_arrays(grid, vm=vmt, va_deg=vat, flatstart=True)     # cnet.flatstart = true on the template copy
+                eng = Engine(a3, **opts)
+                raw2 = eng.solve_outages([lists[i] for i in again], want_v=True, want_types=return_raw)
+                for j, i in enumerate(again):
+                    it1 = int(raw["iterations"][i])
+                    for key, arr in raw.items():
+                        if arr is not None and raw2.get(key) is not None:
+                            arr[i] = raw2[key][j]
+                    raw["iterations"][i] += it1
     finally:
         eng.close()
     out = []

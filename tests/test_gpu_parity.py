@@ -444,3 +444,21 @@ def test_randomised_grids_and_symbolic_options_parity():
             if o.converged:
                 assert np.max(np.abs(raw["V"][i] - o.V)) <= VTOL, tag
                 assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8)), tag
+
+
+def test_retry_flat_start_matches_reference_semantics():
+    """runContingencies!(...; retry_flat_start = true) (contingency.jl:195-207): a non-converged case gets exactly one
+    second attempt from a flat start and reports the summed iterations; converged cases are untouched."""
+    for g in (G.case14(), G.diverge_ring()):
+        cases = api.generateN1Branches(g)
+        plain = api.runContingenciesBatched(g, cases)
+        retry = api.runContingenciesBatched(g, cases, retry_flat_start=True)
+        oc = O.generate_n1_branches(g)
+        want = O.run_contingencies(g, oc, retry_flat_start=True)
+        assert any(not r.converged for r in plain)
+        for p, r, w in zip(plain, retry, want):
+            assert r.converged == w.converged and r.iterations == w.iterations and r.error == w.error
+            if p.converged:
+                assert r.iterations == p.iterations and r.max_vm_pu == p.max_vm_pu
+            elif p.error.startswith("power flow did not converge"):
+                assert r.iterations > p.iterations

@@ -212,3 +212,13 @@ def test_symbolic_selftest_on_irregular_grids(n, seed):
         info, res = api.analyze_only(a.Y, a.slack, ordering=ordering)
         assert res < 1e-10, (ordering, res)
         assert info["nnz_lu_scalar"] >= info["nnz_j_scalar"]
+
+
+def test_oracle_retry_flat_start_sums_iterations():
+    g = G.diverge_ring()
+    cases = O.generate_n1_branches(g)
+    r0 = O.run_contingencies(g, cases)
+    r1 = O.run_contingencies(g, cases, retry_flat_start=True)
+    bad = [i for i, r in enumerate(r0) if not r.converged]
+    assert bad and all(r1[i].iterations == r0[i].iterations + 30 and not r1[i].converged for i in bad)
+    assert all(r1[i].iterations == r0[i].iterations for i in range(len(cases)) if i not in bad)
