@@ -462,3 +462,36 @@ def test_retry_flat_start_matches_reference_semantics():
                 assert r.iterations == p.iterations and r.max_vm_pu == p.max_vm_pu
             elif p.error.startswith("power flow did not converge"):
                 assert r.iterations > p.iterations
+
+
+@pytest.mark.parametrize("variant", ["damped", "no_qlimits", "late_qlimits", "hysteresis_reenable", "loose_tol_short"])
+def test_runpf_keyword_variants_parity(variant):
+    """The runpf! keywords the contingency path forwards (rectangular_network_solver.jl:1783-1883): damping, Q-limit
+    switch, first eligible iteration, hysteresis / cooldown re-enable (limits.jl:527-561), tolerance and iteration cap."""
+    g = G.tiled_grid(rows=12, cols=12, augment=True, pv_every=4, pv_q_mvar=22.0, rating_mva=60.0)
+    okw, ekw = {}, {}
+    if variant == "damped":
+        okw, ekw = dict(damp=0.7), dict(damp=0.7)
+    elif variant == "no_qlimits":
+        okw, ekw = dict(qlimits_enabled=False), dict(qlimits_enabled=0)
+    elif variant == "late_qlimits":
+        okw, ekw = dict(qlimit_start_iter=4), dict(qlimit_start_iter=4)
+    elif variant == "hysteresis_reenable":
+        g.q_hyst_pu, g.cooldown_iters = 0.02, 2
+    elif variant == "loose_tol_short":
+        okw, ekw = dict(tol=1e-5, maxiter=6), dict(tol=1e-5, max_iter=6)
+    vm, va, flat, base = O.solve_base(g, **okw)
+    a = M.build_arrays(g, vm=vm, va_deg=va, flatstart=flat)
+    eng = api.Engine(a, cooldown_iters=g.cooldown_iters, q_hyst_pu=g.q_hyst_pu, **ekw)
+    cases = [[k] for k in range(0, g.nbranch, 5)] + [[3, 77], [10, 11]]
+    raw = eng.solve_outages(cases)
+    eng.close()
+    nsw = 0
+    for i, c in enumerate(cases):
+        o = O.runpf(g, vm, va, c, flatstart=flat, **okw)
+        assert bool(raw["converged"][i]) == o.converged and int(raw["iterations"][i]) == o.iters, (variant, c, raw["iterations"][i], o.iters)
+        if o.converged:
+            assert np.max(np.abs(raw["V"][i] - o.V)) <= VTOL, (variant, c)
+            assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8)), (variant, c)
+        nsw += int(raw["n_switch_events"][i])
+    assert (nsw == 0) == (variant == "no_qlimits")
