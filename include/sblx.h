@@ -213,6 +213,10 @@ int sblx_debug_host_selftest(const sblx_handle* h, uint64_t seed, double* rel_re
 int sblx_analyze_only(int64_t n, const int64_t* colptr, const int64_t* rowval, int64_t slack_idx,
                       const sblx_options* opts, sblx_info* info, double* selftest_residual);
 
+/* Instrumentation: per size class (5) x phase (10) cycle sums of k_front, thread 0's view; only filled by a build with
+ * -DSBLX_PHASE_TIMING (tools/phase_timing.py), SBLX_E_ARG otherwise.  `out50` receives 50 doubles. */
+int sblx_debug_phase_cycles(double* out50);
+
 #ifdef __cplusplus
 }
 #endif
