@@ -225,6 +225,34 @@ class Engine:
         L.check(self.lib.sblx_solve_injections(self.h, B, L.ptr(S.view(np.float64), L.c_f64p), L.ptr(ql, L.c_f64p), C.byref(s)), self.h)
         return r
 
+    def injection_sweep(self, s_spec0, qload0, n_scen, seed=20260724, sigma=0.1, lo=0.5, hi=1.5, chunk=4096):
+        """Load / injection sweep of BASELINE config 4: per scenario an independent truncated-normal factor
+        f ~ N(1, sigma) clipped to [lo, hi] on P and Q of every load bus (the reference's Monte-Carlo recipe,
+        examples/powerflow/mc_probabilistic_powerflow.jl:28-41), solved in chunks so that the per-scenario
+        injection matrices never exceed chunk x n.  Returns the per-scenario summary arrays (no voltages)."""
+        rng = np.random.Generator(np.random.PCG64(seed))
+        s0 = np.asarray(s_spec0, np.complex128)
+        q0 = np.asarray(qload0, float)
+        isload = s0.real < 0
+        keys = ("converged", "status", "iterations", "n_switch_events", "final_mismatch", "vmin_pu", "vmax_pu", "max_loading_pct")
+        out = {k: [] for k in keys}
+        def draw(nb):
+            f = np.clip(rng.normal(1.0, sigma, size=(nb, self.n)), lo, hi)
+            return np.where(isload, s0 * f, s0), np.where(isload, q0 * f, q0)
+
+        from concurrent.futures import ThreadPoolExecutor
+        sizes = [min(chunk, n_scen - b0) for b0 in range(0, n_scen, chunk)]
+        with ThreadPoolExecutor(1) as pool:            # the next chunk is drawn while the GPU solves this one
+            nxt = pool.submit(draw, sizes[0])
+            for i, nb in enumerate(sizes):
+                S, ql = nxt.result()
+                if i + 1 < len(sizes):
+                    nxt = pool.submit(draw, sizes[i + 1])
+                r = self.solve_injections(S, ql, want_v=False, want_types=False)
+                for k in keys:
+                    out[k].append(r[k])
+        return {k: np.concatenate(v) for k, v in out.items()}
+
     def solve_one(self, v_start=None):
         vout = np.zeros(self.n, np.complex128)
         c = C.c_uint8()

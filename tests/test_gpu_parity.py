@@ -495,3 +495,23 @@ def test_runpf_keyword_variants_parity(variant):
             assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8)), (variant, c)
         nsw += int(raw["n_switch_events"][i])
     assert (nsw == 0) == (variant == "no_qlimits")
+
+
+def test_injection_sweep_helper_is_chunk_independent():
+    """Engine.injection_sweep draws the config-4 factors in chunks while the GPU solves the previous chunk; the
+    result must not depend on the chunk size and must equal a direct solve with the same factors."""
+    g = G.tiled_grid(rows=9, cols=9, augment=True, pv_every=3, pv_q_mvar=20.0)
+    vm, va, flat, base = O.solve_base(g)
+    a = M.build_arrays(g, vm=vm, va_deg=va)
+    eng = api.Engine(a)
+    r1 = eng.injection_sweep(a.s_spec, a.qload, 70, seed=3, chunk=1000)
+    r2 = eng.injection_sweep(a.s_spec, a.qload, 70, seed=3, chunk=70)
+    rng = np.random.Generator(np.random.PCG64(3))
+    f = np.clip(rng.normal(1.0, 0.1, size=(70, g.n)), 0.5, 1.5)
+    isload = a.s_spec.real < 0
+    r3 = eng.solve_injections(np.where(isload, a.s_spec * f, a.s_spec), np.where(isload, a.qload * f, a.qload))
+    eng.close()
+    for k in ("converged", "iterations", "n_switch_events", "vmin_pu", "vmax_pu"):
+        assert np.array_equal(r1[k], r2[k]) and np.array_equal(r1[k], r3[k]), k
+    o = O.runpf(g, vm, va, (), s_override=np.where(isload, a.s_spec * f[5], a.s_spec), qload_override=np.where(isload, a.qload * f[5], a.qload))
+    assert o.converged == bool(r1["converged"][5]) and o.iters == int(r1["iterations"][5])
