@@ -515,3 +515,28 @@ def test_injection_sweep_helper_is_chunk_independent():
         assert np.array_equal(r1[k], r2[k]) and np.array_equal(r1[k], r3[k]), k
     o = O.runpf(g, vm, va, (), s_override=np.where(isload, a.s_spec * f[5], a.s_spec), qload_override=np.where(isload, a.qload * f[5], a.qload))
     assert o.converged == bool(r1["converged"][5]) and o.iters == int(r1["iterations"][5])
+
+
+@pytest.mark.parametrize("name,maker", [("case14_n1_oracle.json", lambda: G.case14()),
+                                        ("test3bus_q15_n1_oracle.json", lambda: G.test3bus(qlim_min=-15.0, qlim_max=15.0)),
+                                        ("island_chain_pv_n1_oracle.json", lambda: G.island_chain(True))])
+def test_engine_matches_committed_golden_vectors(name, maker):
+    """The engine against the committed vectors of tests/golden (no oracle code on this test's path)."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+    g = maker()
+    eng = api.Engine(M.build_arrays(g))
+    Vb, conv, itb, *_ = eng.solve_one(None)
+    assert conv and itb == gold["base_iterations"] and np.max(np.abs(np.abs(Vb) - gold["base_vm"])) <= VTOL
+    a = M.build_arrays(g, vm=np.abs(Vb), va_deg=np.degrees(np.angle(Vb)))
+    eng.set_v0(a.v0)
+    raw = eng.solve_outages([c["removed"] for c in gold["cases"]])
+    eng.close()
+    for i, c in enumerate(gold["cases"]):
+        assert bool(raw["converged"][i]) == c["converged"] and int(raw["island_count"][i]) == c["island_count"]
+        if c["error"] != "islanded without reference":
+            assert int(raw["iterations"][i]) == c["iterations"]
+        if c["converged"]:
+            assert np.max(np.abs(np.abs(raw["V"][i]) - c["vm"])) <= VTOL
+            assert raw["bus_type_final"][i].tolist() == c["types"]
+            assert abs(raw["vmin_pu"][i] - c["vmin"]) <= 1e-9 and abs(raw["vmax_pu"][i] - c["vmax"]) <= 1e-9

@@ -222,3 +222,24 @@ def test_oracle_retry_flat_start_sums_iterations():
     bad = [i for i, r in enumerate(r0) if not r.converged]
     assert bad and all(r1[i].iterations == r0[i].iterations + 30 and not r1[i].converged for i in bad)
     assert all(r1[i].iterations == r0[i].iterations for i in range(len(cases)) if i not in bad)
+
+
+GOLDEN = {"case14_n1_oracle.json": lambda: G.case14(), "test3bus_q15_n1_oracle.json": lambda: G.test3bus(qlim_min=-15.0, qlim_max=15.0),
+          "island_chain_pv_n1_oracle.json": lambda: G.island_chain(True)}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_oracle_reproduces_committed_golden_vectors(name):
+    """tests/golden/*.json (written by tests/golden/make_golden.py) pin the oracle against drift."""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+    g = GOLDEN[name]()
+    cases = [c["removed"] for c in gold["cases"]]
+    vm, va, flat, base = O.solve_base(g)
+    assert base.iters == gold["base_iterations"]
+    np.testing.assert_allclose(np.abs(base.V), gold["base_vm"], rtol=0, atol=1e-10)
+    for c, r in zip(gold["cases"], O.run_contingencies(g, cases)):
+        assert (r.converged, r.iterations, r.island_count, r.error) == (c["converged"], c["iterations"], c["island_count"], c["error"])
+        if c["converged"]:
+            np.testing.assert_allclose(np.abs(r.V), c["vm"], rtol=0, atol=1e-10)
+            assert [int(t) for t in r.types] == c["types"]
