@@ -1104,7 +1104,7 @@ static void run_staged(sblx_handle* h) {
     st.scenario_iterations += nstep;
     CK(cudaEventRecord(ev[3], s));
     if (nstep > 0) {
-      dim3 g((nnzB + 7) / 8, (nstep + 31) / 32);
+      dim3 g((nnzB + 31) / 32, (nstep + 31) / 32);
       k_jacobian<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
       st.launches++;
     }
@@ -1600,7 +1600,7 @@ int sblx_debug_newton_step(sblx_handle* h, int64_t nout, const int32_t* outage_b
   int zero = 0;
   CK(cudaMemcpyAsync(h->l_counts.p, one, sizeof one, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->l_step.p, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
-  k_jacobian<<<dim3((nnzB + 7) / 8, 1), dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+  k_jacobian<<<dim3((nnzB + 31) / 32, 1), dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
   launch_factor(h, 1);
   for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
     for (const LaunchGroup& g : h->solve_groups[l]) {

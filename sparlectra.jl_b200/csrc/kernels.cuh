@@ -459,56 +459,79 @@ __global__ void __launch_bounds__(1024) k_decide(DevModel M, Slots A, Lists L) {
 
 // ------------------------------------------------------------------------------------------
 // K2: Jacobian 2x2 blocks into the fixed superset pattern.
-// grid (ceil(nnzB/8), ceil(nStep/32)), block (32, 8): lane = scenario, ty = block entry
+// grid (ceil(nnzB/32), ceil(nStep/32)), block (32, 8): one CTA = 32 scenarios x 32 block entries.
+// Compute phase: lane = scenario (the per-bus state is scenario-interleaved: coalesced reads, shared Ybus
+// values are warp broadcasts), 4 entries per thread, blocks parked in a padded shared-memory tile.
+// Store phase: lane = entry, so each warp writes 1 KB of one scenario's contiguous Jacobian row
+// (the Jacobian is scenario-major for the factorisation) with 256-bit stores.
 // block = [dP/dVr dP/dVi ; dQ/dVr dQ/dVi]  (PV: second row = d|V|/dVr, d|V|/dVi on the diagonal)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_jacobian(DevModel M, Slots A, Lists L) {
+  __shared__ double2 tile[32][33][2];                  // [scenario][entry (+1 pad)][block row]
+  __shared__ int slots[32];
   const int ns = L.counts[2];
   const int li = blockIdx.y * 32 + threadIdx.x;
-  const int ent = blockIdx.x * 8 + threadIdx.y;
-  if (li >= ns || ent >= M.nnzB) return;
-  const int slot = L.step[li];
+  const bool live = li < ns;
+  const int slot = live ? L.step[li] : 0;
+  if (threadIdx.y == 0) slots[threadIdx.x] = live ? slot : -1;
   const size_t W = M.W;
-  const int i = M.bus_of_node[M.jb_row[ent]], j = M.bus_of_node[M.jb_col[ent]];
-  const size_t ki = (size_t)i * W + slot;
-  double b00 = 0, b01 = 0, b10 = 0, b11 = 0;
-  const bool isoi = A.iso[ki] != 0, isoj = A.iso[(size_t)j * W + slot] != 0;
-  if (isoi || isoj || A.type[ki] == T_SLACK) {
-    if (i == j) { b00 = 1.0; b11 = 1.0; }              // neutral identity row (isolated bus / promoted island reference): delta = 0
-  } else {
-    double2 y = M.y_val[M.jb_ypos[ent]];
-    const int no = A.out_cnt[slot];
-    for (int o = 0; o < no; ++o) {
-      const int br = A.out_br[slot * MAXOUT + o];
-      const int f = M.br_from[br], t = M.br_to[br];
-      if (i == j) {
-        if (i == f) y = csub(y, M.y11[br]);
-        else if (i == t) y = csub(y, M.y22[br]);
-      } else if (i == f && j == t) y = csub(y, M.y12[br]);
-      else if (i == t && j == f) y = csub(y, M.y21[br]);
-    }
-    const double2 Vi = A.V[ki];
-    const double2 a = cmul(Vi, cconj(y));        // A = V_i conj(Y_ij)
-    double2 dvr = a;                              // dS/dVr
-    double2 dvi = make_double2(a.y, -a.x);        // dS/dVi = i*(-A)
-    if (i == j) {
-      const double2 I = A.I[ki];
-      dvr.x += I.x; dvr.y -= I.y;                 // + conj(I)
-      dvi.x += I.y; dvi.y += I.x;                 // + i*conj(I)
-    }
-    b00 = dvr.x; b01 = dvi.x;
-    if (A.type[ki] == T_PV) {
-      if (i == j) {
-        const double vm = sqrt(Vi.x * Vi.x + Vi.y * Vi.y);
-        const double d = vm > 0.0 ? vm : 1e-9;    // vm_eps (rectangular_jacobian_builders.jl:362)
-        b10 = Vi.x / d; b11 = Vi.y / d;
-      }
+  const int ent0 = blockIdx.x * 32;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = threadIdx.y + 8 * q, ent = ent0 + e;
+    if (!live || ent >= M.nnzB) continue;
+    const int i = M.bus_of_node[M.jb_row[ent]], j = M.bus_of_node[M.jb_col[ent]];
+    const size_t ki = (size_t)i * W + slot;
+    double b00 = 0, b01 = 0, b10 = 0, b11 = 0;
+    const bool isoi = A.iso[ki] != 0, isoj = A.iso[(size_t)j * W + slot] != 0;
+    if (isoi || isoj || A.type[ki] == T_SLACK) {
+      if (i == j) { b00 = 1.0; b11 = 1.0; }              // neutral identity row (isolated bus / promoted island reference): delta = 0
     } else {
-      b10 = dvr.y; b11 = dvi.y;
+      double2 y = M.y_val[M.jb_ypos[ent]];
+      const int no = A.out_cnt[slot];
+      for (int o = 0; o < no; ++o) {
+        const int br = A.out_br[slot * MAXOUT + o];
+        const int f = M.br_from[br], t = M.br_to[br];
+        if (i == j) {
+          if (i == f) y = csub(y, M.y11[br]);
+          else if (i == t) y = csub(y, M.y22[br]);
+        } else if (i == f && j == t) y = csub(y, M.y12[br]);
+        else if (i == t && j == f) y = csub(y, M.y21[br]);
+      }
+      const double2 Vi = A.V[ki];
+      const double2 a = cmul(Vi, cconj(y));        // A = V_i conj(Y_ij)
+      double2 dvr = a;                              // dS/dVr
+      double2 dvi = make_double2(a.y, -a.x);        // dS/dVi = i*(-A)
+      if (i == j) {
+        const double2 I = A.I[ki];
+        dvr.x += I.x; dvr.y -= I.y;                 // + conj(I)
+        dvi.x += I.y; dvi.y += I.x;                 // + i*conj(I)
+      }
+      b00 = dvr.x; b01 = dvi.x;
+      if (A.type[ki] == T_PV) {
+        if (i == j) {
+          const double vm = sqrt(Vi.x * Vi.x + Vi.y * Vi.y);
+          const double d = vm > 0.0 ? vm : 1e-9;    // vm_eps (rectangular_jacobian_builders.jl:362)
+          b10 = Vi.x / d; b11 = Vi.y / d;
+        }
+      } else {
+        b10 = dvr.y; b11 = dvi.y;
+      }
     }
+    tile[threadIdx.x][e][0] = make_double2(b00, b01);
+    tile[threadIdx.x][e][1] = make_double2(b10, b11);
   }
-  double2* out = reinterpret_cast<double2*>(A.Jv + ((size_t)slot * M.nnzB + ent) * 4);
-  stg_blk(out, make_double2(b00, b01), make_double2(b10, b11));
+  __syncthreads();
+  const int e = threadIdx.x, ent = ent0 + e;
+  if (ent >= M.nnzB) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int sc = threadIdx.y + 8 * q;
+    const int sl = slots[sc];
+    if (sl < 0) continue;
+    double2* out = reinterpret_cast<double2*>(A.Jv + ((size_t)sl * M.nnzB + ent) * 4);
+    stg_blk(out, tile[sc][e][0], tile[sc][e][1]);
+  }
 }
 
 #ifdef SBLX_PHASE_TIMING
