@@ -335,6 +335,7 @@ struct LaunchGroup {
   int subst_chunks = 0, schur_tiles = 0, wmax = 0;   // split path: grid.z of k_subst / k_schur, widest panel
   int lanes = 0;              // k_front: lanes per scenario (< nt: several scenarios share one warp)
   int wide = 0;               // k_front<64>: pivot blocks of 9..16 buses
+  int reg = 0;                // k_front_reg: tiny fronts held in registers
 };
 
 struct HostResults {
@@ -365,7 +366,7 @@ struct sblx_handle {
   DevBuf<unsigned char> d_type0, d_lock, d_br_status;
   DevBuf<int> d_br_from, d_br_to;
   DevBuf<PanelDev> d_panels, d_panels_lv;     // by panel id / in level_panels order (contiguous per launch group)
-  DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels, d_ing_ptr, d_ing_src, d_ing_pairs, d_ing_xptr, d_ing_xsrc, d_vec_ptr, d_vec_src;
+  DevBuf<int> d_struct, d_child, d_rel, d_kpiv, d_inv, d_asm_src, d_asm_dst, d_level_panels, d_ing_ptr, d_ing_src, d_ing_pairs, d_reg_words, d_reg_vptr, d_reg_vsrc, d_ing_xptr, d_ing_xsrc, d_vec_ptr, d_vec_src;
   DevBuf<ChildDev> d_childdev;
   DevBuf<long long> d_rel_ptr, d_inv_ptr;
   std::vector<std::vector<LaunchGroup>> front_groups;   // per level
@@ -460,7 +461,7 @@ static void upload_model(sblx_handle* h) {
   std::vector<PanelDev> pd(S.panels.size());
   for (size_t i = 0; i < pd.size(); ++i) {
     const Panel& P = S.panels[i];
-    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.ing_base, l_off[i], (long long)P.u_off, (long long)P.c_off, (int)P.ingf_base};
+    pd[i] = PanelDev{P.first, P.w, P.h, (int)P.nchild, (int)P.struct_ptr, (int)P.child_ptr, (int)P.ing_base, l_off[i], (long long)P.u_off, (long long)P.c_off, (int)P.ingf_base, (int)P.reg_base, (int)P.reg_vbase, 0};
   }
   h->d_panels.upload(pd, s);
   h->d_struct.upload(S.struct_nodes, s);
@@ -473,6 +474,9 @@ static void upload_model(sblx_handle* h) {
   h->d_ing_ptr.upload(S.ing_ptr, s);
   h->d_ing_src.upload(S.ing_src, s);
   h->d_ing_pairs.upload(S.ing_pairs, s);
+  h->d_reg_words.upload(S.reg_words.empty() ? std::vector<int>(1, 0) : S.reg_words, s);
+  h->d_reg_vptr.upload(S.reg_vptr.empty() ? std::vector<int>(1, 0) : S.reg_vptr, s);
+  h->d_reg_vsrc.upload(S.reg_vsrc.empty() ? std::vector<int>(1, 0) : S.reg_vsrc, s);
   h->d_ing_xptr.upload(S.ing_xptr, s);
   h->d_ing_xsrc.upload(S.ing_xsrc.empty() ? std::vector<int>(1, 0) : S.ing_xsrc, s);
   h->d_vec_ptr.upload(S.vec_ptr, s);
@@ -490,10 +494,11 @@ static void upload_model(sblx_handle* h) {
   h->d_inv_ptr.upload(ip, s);
   // launch groups: per level, panels sorted by size class
   // size class by panel bytes; the two small classes factor the pivot block with an 8-pivot register column
-  // Classes 8/0/1 are the lane-group kernels (4 / 8 / 16 lanes per scenario: pivot blocks of <= 2 / <= 4 / <= 8
+  // Class 9: fronts of <= 8 buses in total, factored in registers (k_front_reg).  Classes 8/0/1 are the lane-group kernels (4 / 8 / 16 lanes per scenario: pivot blocks of <= 2 / <= 4 / <= 8
   // buses, 8 / 4 / 2 scenarios per warp); classes 2..6 give the whole CTA (32..512 threads) to one front; class 7
   // is the 64-thread kernel with a 16-row register column (small fronts with pivot blocks of 9..16 buses).
   int g8_bytes = 4 * 1024, g16_bytes = 8 * 1024, g4_bytes = 1024;
+  const bool reg_class = getenv("SBLX_NO_REG_CLASS") == nullptr;                // tuning probe
   if (const char* e = getenv("SBLX_G4_KB10")) g4_bytes = atoi(e) * 102;        // tuning probe, tenths of a KB (0 disables the class)
   if (const char* e = getenv("SBLX_G8_KB")) g8_bytes = atoi(e) * 1024;       // tuning probes (0 disables the class)
   if (const char* e = getenv("SBLX_G16_KB")) g16_bytes = atoi(e) * 1024;
@@ -504,15 +509,16 @@ static void upload_model(sblx_handle* h) {
   auto front_class_b = [c2_bytes](int bytes) { return bytes <= 6 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= c2_bytes ? 2 : bytes <= 110 * 1024 ? 3 : 4; };
   auto front_class_p = [&](const Panel& P) {
     const int bytes = panel_smem_bytes(P.w, P.h);
+    if (reg_class && P.reg_base >= 0) return 9;       // w + h <= 8: factored entirely in registers (k_front_reg)
     if (P.w <= 2 && bytes <= g4_bytes) return 8;      // 4 lanes per scenario, 8 scenarios per warp
     if (P.w <= 4 && bytes <= g8_bytes) return 0;
     if (P.w <= 8 && bytes <= g16_bytes) return 1;
     int c = front_class_b(bytes);
     return (P.w > 8 && c < 2) ? 7 : 2 + c;          // 7: small front with a wide pivot block (64 threads, 16-row register column)
   };
-  static const int front_nt[9] = {32, 32, 32, 64, 128, 256, 512, 64, 32};
-  static const int front_g[9] = {8, 16, 32, 64, 128, 256, 512, 64, 4};
-  static const int front_wide[9] = {0, 0, 0, 0, 0, 0, 0, 1, 0};
+  static const int front_nt[10] = {32, 32, 32, 64, 128, 256, 512, 64, 32, 32};
+  static const int front_g[10] = {8, 16, 32, 64, 128, 256, 512, 64, 4, 8};
+  static const int front_wide[10] = {0, 0, 0, 0, 0, 0, 0, 1, 0, 0};
   std::vector<int> lp;
   h->front_groups.assign(S.nlevels, {});
   h->solve_groups.assign(S.nlevels, {});
@@ -534,6 +540,7 @@ static void upload_model(sblx_handle* h) {
       LaunchGroup g{(int)lp.size() + (int)i, (int)(j - i), front_nt[c], smem};
       g.lanes = front_g[c];
       g.wide = front_wide[c];
+      g.reg = c == 9;
       for (size_t q = i; q < j; ++q) {
         const Panel& P = S.panels[ids[q]];
         const int hpad = (P.h + 31) & ~31;
@@ -589,7 +596,7 @@ static void upload_model(sblx_handle* h) {
   M.rel_ptr = h->d_rel_ptr.p; M.kpiv = h->d_kpiv.p; M.inv = h->d_inv.p; M.inv_ptr = h->d_inv_ptr.p;
   M.asm_src = h->d_asm_src.p; M.asm_dst = h->d_asm_dst.p;
   M.ing_ptr = h->d_ing_ptr.p; M.ing_src = h->d_ing_src.p;
-  M.ing_pairs = reinterpret_cast<const int2*>(h->d_ing_pairs.p); M.ing_xptr = h->d_ing_xptr.p; M.ing_xsrc = h->d_ing_xsrc.p; M.vec_ptr = h->d_vec_ptr.p; M.vec_src = h->d_vec_src.p;
+  M.ing_pairs = reinterpret_cast<const int2*>(h->d_ing_pairs.p); M.reg_words = h->d_reg_words.p; M.reg_vptr = h->d_reg_vptr.p; M.reg_vsrc = h->d_reg_vsrc.p; M.ing_xptr = h->d_ing_xptr.p; M.ing_xsrc = h->d_ing_xsrc.p; M.vec_ptr = h->d_vec_ptr.p; M.vec_src = h->d_vec_src.p;
   M.childdev = h->d_childdev.p;
   M.u_blocks = S.u_blocks; M.c_blocks = S.c_blocks + 2; M.l_blocks = h->l_blocks;
   const sblx_options& o = h->opt;
@@ -994,7 +1001,8 @@ static void launch_factor(sblx_handle* h, int nstep) {
       for (const LaunchGroup& g : h->front_groups[l]) {
         switch (g.nt) {
           case 32:
-            if (g.lanes == 4) launch_front<32, 4>(h, g, nstep);
+            if (g.reg) k_front_reg<8, 8><<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off);
+            else if (g.lanes == 4) launch_front<32, 4>(h, g, nstep);
             else if (g.lanes == 8) launch_front<32, 8>(h, g, nstep);
             else if (g.lanes == 16) launch_front<32, 16>(h, g, nstep);
             else launch_front<32>(h, g, nstep);

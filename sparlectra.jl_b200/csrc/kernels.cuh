@@ -32,7 +32,7 @@ struct PanelDev {
   int first, w, h, nchild;
   int struct_ptr, child_ptr, ing_base, l_off;   // l_off: level-local offset (blocks) of this panel's L21 in the Lw workspace
   long long u_off, c_off;
-  int ingf_base, pad_;
+  int ingf_base, reg_base, reg_vbase, pad_;     // reg_*: register-resident class (w + h <= 8), else reg_base = -1
 };
 // per (parent, child) record used by the Schur gather
 struct ChildDev {
@@ -51,7 +51,7 @@ struct DevModel {
   const double* rating; const unsigned char* br_status;
   const PanelDev* panels; const int* struct_nodes; const int* child_list; const int* rel; const long long* rel_ptr;
   const int* kpiv; const int* inv; const long long* inv_ptr; const int* asm_src; const int* asm_dst;
-  const int* ing_ptr; const int* ing_src; const int2* ing_pairs; const int* ing_xptr; const int* ing_xsrc; const int* vec_ptr; const int* vec_src; const ChildDev* childdev;
+  const int* ing_ptr; const int* ing_src; const int2* ing_pairs; const int* reg_words; const int* reg_vptr; const int* reg_vsrc; const int* ing_xptr; const int* ing_xsrc; const int* vec_ptr; const int* vec_src; const ChildDev* childdev;
   long long u_blocks, c_blocks, l_blocks;
   double tol, damp, hyst, vm_min, vm_max, base_mva;
   int max_iter, qlim_enabled, qlim_start, cooldown, guard, freeze, allow_reenable;
@@ -951,6 +951,116 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
 #ifdef SBLX_PHASE_TIMING
   if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[NT == 32 ? 0 : NT == 64 ? 1 : NT == 128 ? 2 : NT == 256 ? 3 : 4][9], 1ull);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------
+// K3r: tiny fronts (w + h <= NF = 8 buses) factored ENTIRELY IN REGISTERS: 8 lanes per scenario, 4 scenarios per
+// one-warp CTA (a 16-lane / 12-bus instantiation needs 168 registers and measured slower than the shared-memory
+// lane-group kernel).  Lane r holds block row r of the full front (pivot rows, structure rows incl. the Schur part) and
+// its rhs / update-vector entry.  Per pivot: the 2x2 pivot block is broadcast, its owner scales its row, the
+// scaled row is broadcast block by block and the lanes below update theirs - no shared memory, no barriers.
+// Same recurrences as k_front (U' = D^-1 U, unscaled multipliers, y' = D^-1 (b - M y')).  On sparse
+// transmission grids most fronts of a minimum-degree tree are in this class.
+// ------------------------------------------------------------------------------------------
+template <int G, int NF>
+__global__ void __launch_bounds__(32, (NF <= 8 ? 16 : 10)) k_front_reg(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels) {
+  constexpr int NG = 32 / G;
+  const int nact = L.counts[2];
+  if ((int)blockIdx.x * NG >= nact) return;
+  const int bscen = min((int)blockIdx.x * NG + (int)threadIdx.x / G, nact - 1);   // past the end: repeat the last one
+  const int slot = L.step[bscen];
+  const PanelDev P = group_panels[blockIdx.y];
+  const int w = P.w, h = P.h, nf = w + h;
+  const int r = threadIdx.x % G;
+  const bool mine = r < nf;
+  const unsigned full = 0xffffffffu;
+  double* Cs = A.C + (size_t)slot * M.c_blocks * 4;
+  const double2* Jv = reinterpret_cast<const double2*>(A.Jv + (size_t)slot * M.nnzB * 4);
+  const double2* Ca = reinterpret_cast<const double2*>(Cs);
+  double2 a0[NF], a1[NF];
+  const int* words = M.reg_words + P.reg_base + r * nf;
+#pragma unroll
+  for (int c = 0; c < NF; ++c) {
+    a0[c] = make_double2(0.0, 0.0);
+    a1[c] = a0[c];
+    if (c < nf && mine) {
+      const int v = words[c];
+      if (v != ING_NONE) {
+        if (v < ING_MULTI) {
+          ldg_blk(v < 0 ? Jv + 2 * (size_t)(~v) : Ca + 2 * (size_t)v, a0[c], a1[c]);
+        } else {
+          const int x = v - ING_MULTI;
+          for (int q = M.ing_xptr[x]; q < M.ing_xptr[x + 1]; ++q) {
+            const int sidx = M.ing_xsrc[q];
+            double2 s0, s1;
+            ldg_blk(sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx, s0, s1);
+            a0[c] = cadd(a0[c], s0); a1[c] = cadd(a1[c], s1);
+          }
+        }
+      }
+    }
+  }
+  double2 b = make_double2(0.0, 0.0);
+  if (mine) {
+    if (r < w) b = A.rhs[(size_t)slot * M.m + P.first + r];
+    const int* vp = M.reg_vptr + P.reg_vbase + r;
+    for (int q = vp[0]; q < vp[1]; ++q) b = cadd(b, Ca[M.reg_vsrc[q]]);
+  }
+  bool sing = false;
+#pragma unroll
+  for (int p = 0; p < NF; ++p) {
+    if (p < w) {
+      const double p00 = __shfl_sync(full, a0[p].x, p, G), p01 = __shfl_sync(full, a0[p].y, p, G);
+      const double p10 = __shfl_sync(full, a1[p].x, p, G), p11 = __shfl_sync(full, a1[p].y, p, G);
+      const double wq = p01 * p10;
+      const double det = fma(p00, p11, -wq) + fma(-p01, p10, wq);      // Kahan: rounding error of the product recovered
+      const bool ok = isfinite(det) && det != 0.0;
+      sing |= !ok;
+      const double sc = ok ? 1.0 / det : 0.0;
+      const double d00 = p11 * sc, d01 = -p01 * sc, d10 = -p10 * sc, d11 = p00 * sc;
+      if (r == p) {                                   // the pivot's owner scales its row and its rhs
+#pragma unroll
+        for (int c = 0; c < NF; ++c)
+          if (c > p && c < nf) {
+            const double2 t0 = a0[c], t1 = a1[c];
+            a0[c] = make_double2(d00 * t0.x + d01 * t1.x, d00 * t0.y + d01 * t1.y);
+            a1[c] = make_double2(d10 * t0.x + d11 * t1.x, d10 * t0.y + d11 * t1.y);
+          }
+        b = make_double2(d00 * b.x + d01 * b.y, d10 * b.x + d11 * b.y);
+      }
+      const bool below = r > p && mine;
+      const double2 m0 = a0[p], m1 = a1[p];           // this lane's multiplier block A_rp (unscaled)
+      const double yx = __shfl_sync(full, b.x, p, G), yy = __shfl_sync(full, b.y, p, G);
+      if (below) {
+        b.x = fma(-m0.x, yx, b.x); b.x = fma(-m0.y, yy, b.x);
+        b.y = fma(-m1.x, yx, b.y); b.y = fma(-m1.y, yy, b.y);
+      }
+#pragma unroll
+      for (int c = 0; c < NF; ++c)
+        if (c > p && c < nf) {
+          double2 u0, u1;
+          u0.x = __shfl_sync(full, a0[c].x, p, G); u0.y = __shfl_sync(full, a0[c].y, p, G);
+          u1.x = __shfl_sync(full, a1[c].x, p, G); u1.y = __shfl_sync(full, a1[c].y, p, G);
+          if (below) bmsub(a0[c], a1[c], m0, m1, u0, u1);
+        }
+    }
+  }
+  if (sing && r == 0) atomicOr(&A.singular[slot], 1);
+  // ---- outputs: U' rows and y' of the pivots, update matrix + update vector of the structure rows
+  if (r < w) {
+    double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4) + 2 * (size_t)(r * nf);
+#pragma unroll
+    for (int c = 0; c < NF; ++c)
+      if (c < nf && c > r) stg_blk(U + 2 * c, a0[c], a1[c]);
+    A.yv[(size_t)slot * M.m + P.first + r] = b;
+  } else if (mine) {
+    double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
+    double2* row = Co + 2 * (size_t)((r - w) * h);
+#pragma unroll
+    for (int c = 0; c < NF; ++c)
+      if (c < nf && c >= w) stg_blk(row + 2 * (c - w), a0[c], a1[c]);
+    Co[2 * (size_t)h * h + (r - w)] = b;
+  }
 }
 
 // ==========================================================================================

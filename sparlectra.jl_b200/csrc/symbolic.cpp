@@ -655,6 +655,9 @@ static void build_from_order(int m, const std::vector<int64_t>& rowptr, const st
     S.ing_xsrc.clear();
     S.vec_ptr.assign(m + 1, 0);
     S.vec_src.clear();
+    S.reg_words.clear();
+    S.reg_vptr.clear();
+    S.reg_vsrc.clear();
     std::vector<std::vector<int>> vsrc(m);
     for (int p = 0; p < np; ++p) {
       Panel& P = S.panels[p];
@@ -678,6 +681,44 @@ static void build_from_order(int m, const std::vector<int64_t>& rowptr, const st
           }
         const int64_t vbase = 2 * (C.c_off + (int64_t)hc * hc);
         for (int a = 0; a < kc; ++a) vsrc[P.first + rel[a]].push_back((int)(vbase + a));
+      }
+      P.reg_base = -1;
+      if (nf <= 8) {       // register-resident class: sources of the full nf x nf front, row-major, and per-row vector sources
+        std::vector<std::vector<int>> full((size_t)nf * nf), fv(nf);
+        for (int k = 0; k < nblk; ++k) {
+          int r, c2;
+          if (k < w * nf) { r = k / nf; c2 = k - r * nf; }
+          else { const int q = k - w * nf, lj = q / h, li = q - lj * h; r = w + li; c2 = lj; }
+          full[(size_t)r * nf + c2] = src[k];
+        }
+        for (int ci = 0; ci < P.nchild; ++ci) {
+          const int c = S.child_list[P.child_ptr + ci];
+          const Panel& C = S.panels[c];
+          const int hc = C.h, kc = S.kpiv[c];
+          const int* rel = &S.rel[S.rel_ptr[c]];
+          for (int a = kc; a < hc; ++a)
+            for (int b = kc; b < hc; ++b) full[(size_t)rel[a] * nf + rel[b]].push_back((int)(C.c_off + (int64_t)a * hc + b));
+          const int64_t vbase = 2 * (C.c_off + (int64_t)hc * hc);
+          for (int a = 0; a < hc; ++a) fv[rel[a]].push_back((int)(vbase + a));
+        }
+        P.reg_base = (int64_t)S.reg_words.size();
+        for (auto& f : full) {
+          int word;
+          if (f.empty()) word = ING_NONE;
+          else if (f.size() == 1) word = f[0];
+          else {
+            word = ING_MULTI + (int)S.ing_xptr.size() - 1;
+            for (int v : f) S.ing_xsrc.push_back(v);
+            S.ing_xptr.push_back((int)S.ing_xsrc.size());
+          }
+          S.reg_words.push_back(word);
+        }
+        P.reg_vbase = (int64_t)S.reg_vptr.size();
+        for (int r = 0; r < nf; ++r) {
+          S.reg_vptr.push_back((int)S.reg_vsrc.size());
+          for (int v : fv[r]) S.reg_vsrc.push_back(v);
+        }
+        S.reg_vptr.push_back((int)S.reg_vsrc.size());
       }
       P.ing_base = (int64_t)S.ing_ptr.size();
       P.ingf_base = (int64_t)S.ing_pairs.size() / 2;

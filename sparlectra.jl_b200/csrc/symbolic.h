@@ -39,6 +39,8 @@ struct Panel {
   int64_t asm_ptr = 0, asm_cnt = 0;   // original Jacobian blocks assembled here
   int64_t ing_base = 0;               // first entry of this panel in ing_ptr (w*(w+h) + h*w + 1 entries)
   int64_t ingf_base = 0;              // first (source, destination) pair of this panel in ing_pairs (w*(w+h) + h*w pairs)
+  int64_t reg_base = -1;              // register-resident class (w + h <= 8): first word in reg_words ((w+h)^2 words), else -1
+  int64_t reg_vbase = 0;              //   ... and first entry in reg_vptr (w + h + 1 entries)
 };
 
 struct Symbolic {
@@ -68,6 +70,10 @@ struct Symbolic {
   // two), or ING_MULTI + x with the sources in ing_xsrc[ing_xptr[x] .. ing_xptr[x+1]); destination: block index in
   // the shared-memory panel
   std::vector<int> ing_pairs, ing_xptr, ing_xsrc;
+  // register-resident tiny fronts (w + h <= 8): source word of EVERY block of the full front, row-major (pivot rows,
+  // then structure rows incl. the Schur part = the children's contributions), same word encoding; and per front row
+  // the update-vector / rhs contributions of the children (double2 indices into the arena)
+  std::vector<int> reg_words, reg_vptr, reg_vsrc;
   // rhs of the pivots: per elimination index the CSR list of update-vector entries (double2 index in the arena)
   std::vector<int> vec_ptr, vec_src;
   // levels
