@@ -21,6 +21,7 @@ eng.run_staged()
 t = []
 for _ in range(3):
     eng.run_staged(); st = eng.stats(); t.append(st["total_ms"])
+print("run totals ms:", [round(x, 1) for x in t], "ticks", st["ticks"], "launches", st["launches"])
 res = eng.fetch(); info = eng.info()
 ms = float(np.median(t))
 print(f"{g.name} {opts}: buses {g.n} branches {g.nbranch} base conv {conv} it {it}; scenarios {len(cases)} ({rep}x N-1) converged {int(res['converged'].sum())} "
