@@ -7,6 +7,7 @@ from sblx import api, grid as G, model as M
 spec = (sys.argv[1] if len(sys.argv) > 1 else "random:2869:3").split(":")
 g = G.random_meshed_grid(int(spec[1]), int(spec[2]), gen_share=1.01) if spec[0] == "random" else G.tiled_grid(rows=int(spec[1]), cols=int(spec[2]), augment=True)
 opts = dict(kv.split("=") for kv in sys.argv[2:])
+nmax = int(opts.pop("nmax", 0))
 opts = {k: (float(v) if "." in v else int(v)) for k, v in opts.items()}
 eng = api.Engine(M.build_arrays(g), **opts)
 Vb, conv, it, *_ = eng.solve_one(None)
@@ -15,6 +16,8 @@ eng.set_v0(a.v0)
 cases = [[k] for k in range(g.nbranch)]
 rep = max(1, 20000 // len(cases))
 cases = cases * rep
+if nmax:
+    cases = cases[:: max(1, len(cases) // nmax)][:nmax]
 optr, obr = eng.pack_outages(cases)
 eng.stage_outages(optr, obr)
 eng.run_staged()
