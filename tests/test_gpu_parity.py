@@ -540,3 +540,15 @@ def test_engine_matches_committed_golden_vectors(name, maker):
             assert np.max(np.abs(np.abs(raw["V"][i]) - c["vm"])) <= VTOL
             assert raw["bus_type_final"][i].tolist() == c["types"]
             assert abs(raw["vmin_pu"][i] - c["vmin"]) <= 1e-9 and abs(raw["vmax_pu"][i] - c["vmax"]) <= 1e-9
+
+
+def test_malformed_outage_sets_are_reported_per_scenario():
+    """More than 8 branches in one scenario, or an id outside the model: status 8 for that scenario, the rest of
+    the batch is solved (failures are reported, never thrown: contingency.jl:72-73)."""
+    g = G.tiled_grid(rows=6, cols=6, augment=True)
+    eng = api.Engine(M.build_arrays(g))
+    raw = eng.solve_outages([[0], list(range(9)), [g.nbranch + 5], [], [1, 2]])
+    eng.close()
+    assert raw["status"].tolist()[1] == 8 and raw["status"].tolist()[2] == 8
+    assert not raw["converged"][1] and not raw["converged"][2]
+    assert raw["converged"][0] and raw["converged"][3] and raw["converged"][4]
