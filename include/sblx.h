@@ -55,8 +55,8 @@ enum {
   SBLX_ST_MAX_SWITCHING = 6,           /* :max_switching_exceeded */
   SBLX_ST_ISLANDED_NO_REF = 7,         /* "islanded without reference" (contingency.jl:218-220) */
   SBLX_ST_BAD_BRANCH = 8,              /* unknown / out-of-range branch in the case */
-  SBLX_ST_ISLANDED_UNSUPPORTED = 9     /* splits into >= 2 islands that each own a reference: the
-                                          reference solves them island-wise; this engine flags them */
+  SBLX_ST_ISLANDED_UNSUPPORTED = 9     /* reserved, no longer produced: grids that split into several islands with
+                                          a reference each are solved island-wise like the reference does */
 };
 
 /* error codes */
