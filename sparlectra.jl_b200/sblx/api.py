@@ -491,3 +491,41 @@ def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30
                                      float(raw["vmin_pu"][i]), float(raw["max_loading_pct"][i]), over, viol,
                                      int(raw["island_count"][i]), None))
     return (out, raw) if return_raw else out
+
+
+# ---------------------------------------------------------------------------
+# reporting helpers of the contingency API (host only; src/contingency.jl:321-380)
+# ---------------------------------------------------------------------------
+def _fit_column(s: str, width: int) -> str:
+    return s if len(s) <= width else s[: width - 1] + "~"
+
+
+def printContingencyResults(results, io=None, max_rows: int = 50):
+    """printContingencyResults (src/contingency.jl:329-363): fixed-width table of the cases."""
+    import sys
+    io = io or sys.stdout
+    w = io.write
+    w(f"N-1 contingency results ({len(results)} case(s), {sum(1 for r in results if r.converged)} converged)\n")
+    w("-" * 116 + "\n")
+    w("%-28s %-9s %5s %9s %9s %12s %8s %8s %7s  %s\n" % ("case", "converged", "iter", "Vmin[pu]", "Vmax[pu]", "loading[%]", "overld", "V-viol", "islands", "error"))
+    w("-" * 116 + "\n")
+    fmt = lambda x, f: "-" if (x is None or math.isnan(x)) else f % x
+    for r in results[:max_rows]:
+        w("%-28s %-9s %5d %9s %9s %12s %8d %8d %7d  %s\n" % (
+            _fit_column(r.name, 28), "yes" if r.converged else "NO", r.iterations, fmt(r.min_vm_pu, "%.4f"), fmt(r.max_vm_pu, "%.4f"),
+            fmt(r.max_branch_loading_pct, "%.1f"), len(r.overloaded_branches), len(r.voltage_violations), r.island_count, r.error or ""))
+    if len(results) > max_rows:
+        w(f"... {len(results) - max_rows} more row(s) not shown (max_rows = {max_rows})\n")
+    w("-" * 116 + "\n")
+
+
+def writeContingencyResultsCSV(path: str, results) -> str:
+    """writeContingencyResultsCSV (src/contingency.jl:365-380): semicolon-separated, one row per case, input order."""
+    jl = lambda v: ("true" if v else "false") if isinstance(v, (bool, np.bool_)) else ("NaN" if isinstance(v, float) and math.isnan(v) else str(v))
+    with open(path, "w") as f:
+        f.write("name;converged;iterations;min_vm_pu;max_vm_pu;max_branch_loading_pct;overloaded_branches;voltage_violations;island_count;error\n")
+        for r in results:
+            f.write(";".join([r.name, jl(bool(r.converged)), jl(int(r.iterations)), jl(float(r.min_vm_pu)), jl(float(r.max_vm_pu)),
+                              jl(float(r.max_branch_loading_pct)), ",".join(r.overloaded_branches), ",".join(r.voltage_violations),
+                              jl(int(r.island_count)), r.error or ""]) + "\n")
+    return path

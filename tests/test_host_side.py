@@ -243,3 +243,22 @@ def test_oracle_reproduces_committed_golden_vectors(name):
         if c["converged"]:
             np.testing.assert_allclose(np.abs(r.V), c["vm"], rtol=0, atol=1e-10)
             assert [int(t) for t in r.types] == c["types"]
+
+
+def test_contingency_reporting_helpers(tmp_path):
+    """printContingencyResults / writeContingencyResultsCSV (src/contingency.jl:321-380) on hand-made results."""
+    import io
+    rs = [api.ContingencyResult("B_ACL_1_2", True, 4, 1.06, 0.98123, 87.25, [], ["Bus9"], 1, None),
+          api.ContingencyResult("a_very_long_contingency_case_name_that_overflows", False, 30, float("nan"), float("nan"), float("nan"), [], [], 2,
+                                "power flow did not converge (status 1)")]
+    buf = io.StringIO()
+    api.printContingencyResults(rs, io=buf, max_rows=1)
+    out = buf.getvalue().splitlines()
+    assert out[0] == "N-1 contingency results (2 case(s), 1 converged)"
+    assert "yes" in out[4] and "0.9812" in out[4] and "87.2" in out[4]          # %.1f of 87.25 (round-half-even)
+    assert out[5].startswith("... 1 more row(s) not shown")
+    p = api.writeContingencyResultsCSV(str(tmp_path / "r.csv"), rs)
+    rows = open(p).read().splitlines()
+    assert rows[0].startswith("name;converged;iterations")
+    assert rows[1] == "B_ACL_1_2;true;4;0.98123;1.06;87.25;;Bus9;1;"
+    assert rows[2].split(";")[1:6] == ["false", "30", "NaN", "NaN", "NaN"]
