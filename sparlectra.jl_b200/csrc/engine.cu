@@ -1227,6 +1227,11 @@ static void fetch_results(sblx_handle* h, sblx_results* res) {
         if (!std::isnan(load[u])) { ld = any_ld ? std::max(ld, load[u]) : load[u]; any_ld = true; }
       }
       if (!c) { f = nan; lo = nan; hi = nan; ld = nan; sw = 0; }
+      // buses outside every island are isolated: they keep 1 angle 0 and type "isolated" like in a single solve
+      if (wantV)
+        for (int b = 0; b < n; ++b) reinterpret_cast<double2*>(res->V)[(size_t)k * n + b] = make_double2(1.0, 0.0);
+      if (wantT)
+        for (int b = 0; b < n; ++b) res->bus_type_final[(size_t)k * n + b] = (uint8_t)T_ISO;
       for (int q = 0; q < R.sub_count[k]; ++q) {
         const int64_t u = R.sub_first[k] + q - B;
         for (int b : R.sub_buses[u]) {

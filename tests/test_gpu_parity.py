@@ -552,3 +552,13 @@ def test_malformed_outage_sets_are_reported_per_scenario():
     assert raw["status"].tolist()[1] == 8 and raw["status"].tolist()[2] == 8
     assert not raw["converged"][1] and not raw["converged"][2]
     assert raw["converged"][0] and raw["converged"][3] and raw["converged"][4]
+
+
+def test_island_wise_solve_with_an_isolated_bus():
+    """N-2 that isolates a leaf bus AND splits the rest into two referenced islands (found by tools/stress.py):
+    the isolated bus keeps 1 angle 0 / type isolated in the recombined island-wise result."""
+    g = G.random_meshed_grid(545, 808968, extra_edge_frac=0.24766309440693596, gen_share=0.9570001040188474)
+    cases = [[383, 643], [383], [643]]
+    raw, oracle, _ = _run_both(g, cases)
+    _compare_batch(g, cases, raw, oracle, "rand545")
+    assert raw["island_count"][0] == 2 and raw["bus_type_final"][0][306] == 0 and raw["V"][0][306] == 1.0
