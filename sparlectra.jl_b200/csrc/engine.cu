@@ -741,7 +741,12 @@ static int analyze_scenario(const HostModel& H, const int* out, int nout, TopoSc
       const int br = out[q];
       if (!H.br_status[br]) continue;
       const int u = H.br_from[br], v = H.br_to[br];
-      if (is_iso(u) || is_iso(v)) continue;
+      if (is_iso(u) || is_iso(v)) {
+        // a leaf bus that lost its only branch cannot disconnect anything else; a bus that lost SEVERAL branches
+        // may have been the only link between its neighbours: full component analysis
+        if ((is_iso(u) && H.deg[u] > 1) || (is_iso(v) && H.deg[v] > 1)) need_full = true;
+        continue;
+      }
       // bidirectional BFS u <-> v in the graph minus the outage set
       const int sa = ++ts.stamp, sb = ++ts.stamp;
       ts.qa.assign(1, u); ts.qb.assign(1, v);

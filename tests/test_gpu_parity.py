@@ -562,3 +562,33 @@ def test_island_wise_solve_with_an_isolated_bus():
     raw, oracle, _ = _run_both(g, cases)
     _compare_batch(g, cases, raw, oracle, "rand545")
     assert raw["island_count"][0] == 2 and raw["bus_type_final"][0][306] == 0 and raw["V"][0][306] == 1.0
+
+
+@pytest.mark.parametrize("args,kw,case", [
+    ((50, 199813), dict(extra_edge_frac=0.2290426133360295, pv_frac=0.20315213184860367, gen_share=0.9051247332382303), [43, 44, 46]),
+    ((65, 250666), dict(extra_edge_frac=0.12247042342733547, pv_frac=0.28330260349118397, gen_share=0.9351149305359199), [7, 15, 21, 65]),
+])
+def test_outage_set_that_isolates_a_cut_bus(args, kw, case):
+    """N-3 / N-4 sets that strip a bus of ALL its branches where that bus was the only link between its neighbours
+    (found by tools/stress_islands.py): the grid splits although every other removed branch still has connected
+    endpoints - the host topology analysis must not take its connected-grid shortcut."""
+    g = G.random_meshed_grid(*args, **kw)
+    cases = [case, case[:1], case[1:]]
+    raw, oracle, _ = _run_both(g, cases)
+    _compare_batch(g, cases, raw, oracle, g.name)
+    assert raw["island_count"][0] == 2
+
+
+def test_topology_heavy_outage_sets_parity():
+    """Nearly radial small grids with N-2..N-4 sets: most scenarios isolate buses and / or split the grid into several
+    islands, with and without a reference (short version of tools/stress_islands.py)."""
+    rng = np.random.default_rng(5)
+    multi = 0
+    for r in range(6):
+        g = G.random_meshed_grid(int(rng.integers(20, 120)), int(rng.integers(1, 10**6)), extra_edge_frac=float(rng.uniform(0.02, 0.25)),
+                                 pv_frac=float(rng.uniform(0.1, 0.4)), gen_share=float(rng.uniform(0.9, 1.0)))
+        cases = [sorted(int(x) for x in rng.choice(g.nbranch, size=int(rng.integers(2, 5)), replace=False)) for _ in range(20)]
+        raw, oracle, _ = _run_both(g, cases)
+        _compare_batch(g, cases, raw, oracle, g.name)
+        multi += int((raw["island_count"] > 1).sum())
+    assert multi > 20
