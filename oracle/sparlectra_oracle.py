@@ -734,7 +734,10 @@ def runpf(grid, vm, va_deg, removed=(), *, maxiter=30, tol=1e-8, damp=1.0, qlimi
         sl = loc[ref]
         V0, _ = initial_vrect(grid, vm[idx], va[idx], t, flat)
         V0[sl] = _mag_keep_angle(V0[sl], vset[idx][sl])
-        r = run_nr(Ysub, V0, S[idx], t, vset[idx], sl, qmin[idx], qmax[idx], ql[idx], **kw)
+        # lock_pv_to_pq_buses is handed unchanged to the island sub-net (rectangular_network_solver.jl:1991): its
+        # indices address the sub-net's own numbering; ids beyond the island's size are ignored (limits.jl:434-438)
+        r = run_nr(Ysub, V0, S[idx], t, vset[idx], sl, qmin[idx], qmax[idx], ql[idx],
+                   lock=tuple(b for b in lock if 0 <= b < len(idx)), **kw)
         total_it += r.iters
         nev += r.n_events
         fm = max(fm, r.history[-1] if r.history else 0.0)

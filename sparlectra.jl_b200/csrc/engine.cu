@@ -390,7 +390,7 @@ struct sblx_handle {
   // staged batch
   int64_t B = 0;
   bool staged = false, ran = false, sweep_q = false;
-  DevBuf<int> b_queue, b_out_ptr, b_out_br, b_iso_ptr, b_iso_bus, b_ref_ptr, b_ref_bus;
+  DevBuf<int> b_queue, b_out_ptr, b_out_br, b_iso_ptr, b_iso_bus, b_ref_ptr, b_ref_bus, b_lk_ptr, b_lk_bus;
   DevBuf<double2> b_S, b_Vstart;
   DevBuf<double> b_ql;
   DevBuf<int> r_conv, r_status, r_iter, r_nsw;
@@ -847,9 +847,11 @@ static void alloc_results(sblx_handle* h, int64_t B, bool want_v, bool want_type
 static void set_batch(sblx_handle* h) {
   Batch& Bt = h->Bt;
   Bt.B = (int)h->hostres.Bint; Bt.nq = (int)h->nq; Bt.use_sweep_q = h->sweep_q;
+  Bt.Btop = h->hostres.sub_first.empty() ? Bt.B : (int)h->hostres.sub_first.size();
   Bt.queue = h->b_queue.p; Bt.out_ptr = h->b_out_ptr.p; Bt.out_br = h->b_out_br.p;
   Bt.iso_ptr = h->b_iso_ptr.p; Bt.iso_bus = h->b_iso_bus.p;
   Bt.ref_ptr = h->b_ref_ptr.p; Bt.ref_bus = h->b_ref_bus.p;
+  Bt.lk_ptr = h->b_lk_ptr.p; Bt.lk_bus = h->b_lk_bus.p;
   Bt.Ssweep = h->b_S.p; Bt.qlsweep = h->b_ql.p; Bt.Vstart = h->b_Vstart.p;
   Bt.r_conv = h->r_conv.p; Bt.r_status = h->r_status.p; Bt.r_iter = h->r_iter.p; Bt.r_nsw = h->r_nsw.p;
   Bt.r_fm = h->r_fm.p; Bt.r_vmin = h->r_vmin.p; Bt.r_vmax = h->r_vmax.p; Bt.r_load = h->r_load.p;
@@ -913,6 +915,12 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   std::vector<int> queue;
   queue.reserve(B);
   std::vector<int> ref_ptr(1, 0), ref_bus;
+  // lock_pv_to_pq_buses in an island-wise solve: the reference hands the list UNCHANGED to every island sub-net
+  // (rectangular_network_solver.jl:1991), where the indices address the sub-net's own bus numbering (the island's
+  // buses in ascending order, ac_islands.jl:329-337; ids beyond the island's size are ignored, limits.jl:434-438)
+  std::vector<int> lk_ptr(1, 0), lk_bus, lock_ids;
+  for (int b = 0; b < H.n; ++b)
+    if (H.lockmask[b]) lock_ids.push_back(b);
   R.sub_first.assign(B, 0);
   R.sub_count.assign(B, 0);
   R.sub_buses.clear();
@@ -941,6 +949,9 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
       iso_ptr.push_back((int)iso_bus.size());
       if (!has_slack) ref_bus.push_back(promoted);
       ref_ptr.push_back((int)ref_bus.size());
+      for (int j : lock_ids)
+        if (j < (int)isl.size()) lk_bus.push_back(isl[j]);
+      lk_ptr.push_back((int)lk_bus.size());
       // same outage list as the parent scenario
       const int ob = out_ptr[s], oe = out_ptr[s + 1];
       for (int q = ob; q < oe; ++q) out_br.push_back(out_br[q]);
@@ -963,6 +974,8 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   h->b_iso_bus.upload(iso_bus, h->stream);
   h->b_ref_ptr.upload(ref_ptr, h->stream);
   h->b_ref_bus.upload(ref_bus, h->stream);
+  h->b_lk_ptr.upload(lk_ptr, h->stream);
+  h->b_lk_bus.upload(lk_bus.empty() ? std::vector<int>(1, 0) : lk_bus, h->stream);
   h->b_S.release(); h->b_ql.release(); h->b_Vstart.release();
   alloc_results(h, Bint, want_v, want_types);
   CK(cudaStreamSynchronize(h->stream));
@@ -1087,7 +1100,7 @@ static void run_staged(sblx_handle* h) {
       k_mismatch<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
       st.launches++;
       if (h->opt.qlimits_enabled) {
-        k_qlimit<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+        k_qlimit<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
         k_norm<<<nactive_ub, 256, 0, s>>>(h->M, h->A, h->L);
         st.launches += 2;
       }

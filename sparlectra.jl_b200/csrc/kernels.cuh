@@ -78,9 +78,11 @@ struct Lists {
 };
 
 struct Batch {
-  int B, nq, use_sweep_q;
+  int B, nq, use_sweep_q;      // B: scenarios on the device (caller scenarios + island sub-scenarios)
+  int Btop;                    // caller scenarios; ids >= Btop are island sub-scenarios
   const int* queue; const int* out_ptr; const int* out_br; const int* iso_ptr; const int* iso_bus;
   const int* ref_ptr; const int* ref_bus;     // per scenario: PV buses promoted to island reference (ac_islands.jl:228-234)
+  const int* lk_ptr; const int* lk_bus;       // per ISLAND sub-scenario (index scen - Btop): its locked PV buses, see stage_outages
   const double2* Ssweep; const double* qlsweep; const double2* Vstart;
   // results
   int* r_conv; int* r_status; int* r_iter; int* r_nsw; double* r_fm; double* r_vmin; double* r_vmax; double* r_load;
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(256) k_mismatch(DevModel M, Slots A, Lists L) 
 // ------------------------------------------------------------------------------------------
 // K5: Q-limit active set. Same mapping as k_mismatch.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_qlimit(DevModel M, Slots A, Lists L) {
+__global__ void __launch_bounds__(256) k_qlimit(DevModel M, Slots A, Lists L, Batch Bt) {
   const int na = L.counts[0];
   const int li = blockIdx.y * 32 + threadIdx.x;
   const int bus = blockIdx.x * 8 + threadIdx.y;
@@ -351,7 +353,13 @@ __global__ void __launch_bounds__(256) k_qlimit(DevModel M, Slots A, Lists L) {
   const double ql = A.qload_s ? A.qload_s[k] : M.qload[bus];
   const double qreq = Sc.y + ql;
   bool touched = false;
-  if (type == T_PV && !M.lockmask[bus]) {
+  bool locked = M.lockmask[bus] != 0;
+  const int scen = A.scen[slot];
+  if (Bt.lk_ptr && scen >= Bt.Btop) {              // island sub-scenario: the lock list addresses the island's own numbering
+    locked = false;
+    for (int q = Bt.lk_ptr[scen - Bt.Btop]; q < Bt.lk_ptr[scen - Bt.Btop + 1]; ++q) locked |= Bt.lk_bus[q] == bus;
+  }
+  if (type == T_PV && !locked) {
     int side = 0;
     double clamp = 0.0;
     if (has_hi && qreq > qmax + M.hyst) { side = 1; clamp = qmax; }

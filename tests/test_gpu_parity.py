@@ -592,3 +592,32 @@ def test_topology_heavy_outage_sets_parity():
         _compare_batch(g, cases, raw, oracle, g.name)
         multi += int((raw["island_count"] > 1).sum())
     assert multi > 20
+
+
+def test_locked_pv_list_in_island_wise_solves_addresses_island_numbering():
+    """lock_pv_to_pq_buses + islanding: the reference hands the list unchanged to each island sub-net
+    (rectangular_network_solver.jl:1991), so an id addresses the island's own bus numbering (ac_islands.jl:329-337)
+    and ids beyond the island's size lock nothing (limits.jl:434-438).  Found by tools/stress_keywords.py."""
+    g = G.random_meshed_grid(237, 637171, pv_q_mvar=30.0, pv_frac=0.2, gen_share=0.95)
+    vm, va, flat, base = O.solve_base(g)
+    a = M.build_arrays(g, vm=vm, va_deg=va, flatstart=flat)
+    pv = np.flatnonzero(a.bus_type == M.BUS_PV)
+    iso_cases = []
+    for k in range(g.nbranch):                     # radial branches: their outage splits the grid
+        o = O.runpf(g, vm, va, [k], flatstart=flat)
+        if o.island_count == 2 and o.reason != O.R_ISLANDED_NO_REF:
+            iso_cases.append([k])
+        if len(iso_cases) >= 6:
+            break
+    assert iso_cases
+    for lock in ([int(pv[0])], [int(pv[-1])], [int(pv[1]), int(pv[len(pv) // 2])]):
+        eng = api.Engine(a)
+        eng.set_locked_pv(lock)
+        raw = eng.solve_outages(iso_cases + [[]])
+        eng.close()
+        for i, c in enumerate(iso_cases + [[]]):
+            o = O.runpf(g, vm, va, c, flatstart=flat, lock=lock)
+            assert bool(raw["converged"][i]) == o.converged, (lock, c)
+            if o.converged:
+                assert int(raw["iterations"][i]) == o.iters and np.max(np.abs(raw["V"][i] - o.V)) <= VTOL, (lock, c)
+                assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8)), (lock, c)
