@@ -216,6 +216,14 @@ int sblx_debug_host_selftest(const sblx_handle* h, uint64_t seed, double* rel_re
 int sblx_analyze_only(int64_t n, const int64_t* colptr, const int64_t* rowval, int64_t slack_idx,
                       const sblx_options* opts, sblx_info* info, double* selftest_residual);
 
+/* Host-only (no CUDA): the per-scenario topology analysis of sblx_solve_outages - island count over the in-service
+ * branches, number of isolated buses, and the verdict: -1 solved as one system on the device, -2 solved island-wise,
+ * SBLX_ST_ISLANDED_NO_REF, SBLX_ST_BAD_BRANCH.  bus_type as in sblx_create (SBLX_BUS_*). */
+int sblx_debug_topology(int64_t n, int64_t slack_idx, const uint8_t* bus_type, int64_t nbranch, const int32_t* br_from,
+                        const int32_t* br_to, const uint8_t* br_status, int32_t index_base, int64_t B,
+                        const int32_t* outage_ptr, const int32_t* outage_branch, int32_t* island_count, int32_t* status,
+                        int32_t* n_isolated);
+
 /* Instrumentation: per size class (5) x phase (10) cycle sums of k_front, thread 0's view; only filled by a build with
  * -DSBLX_PHASE_TIMING (tools/phase_timing.py), SBLX_E_ARG otherwise.  `out50` receives 50 doubles. */
 int sblx_debug_phase_cycles(double* out50);

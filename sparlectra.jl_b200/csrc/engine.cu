@@ -1668,6 +1668,49 @@ int sblx_debug_host_selftest(const sblx_handle* h, uint64_t seed, double* rel_re
   }
 }
 
+int sblx_debug_topology(int64_t n, int64_t slack_idx, const uint8_t* bus_type, int64_t nbranch, const int32_t* br_from,
+                        const int32_t* br_to, const uint8_t* br_status, int32_t index_base, int64_t B, const int32_t* outage_ptr,
+                        const int32_t* outage_branch, int32_t* island_count, int32_t* status, int32_t* n_isolated) {
+  // host-only: the topology analysis stage_outages runs per scenario (isolated buses, islands, reference check)
+  if (n <= 0 || nbranch < 0 || !bus_type || !br_from || !br_to || B < 0 || (B > 0 && !outage_ptr)) return SBLX_E_ARG;
+  try {
+    HostModel H;
+    H.n = (int)n; H.nbr = (int)nbranch; H.slack = (int)(slack_idx - index_base);
+    H.type0.assign(bus_type, bus_type + n);
+    H.br_from.resize(nbranch); H.br_to.resize(nbranch); H.br_status.resize(nbranch);
+    for (int64_t k = 0; k < nbranch; ++k) {
+      H.br_from[k] = br_from[k] - index_base; H.br_to[k] = br_to[k] - index_base;
+      H.br_status[k] = br_status ? (br_status[k] != 0) : 1;
+      if (H.br_from[k] < 0 || H.br_from[k] >= n || H.br_to[k] < 0 || H.br_to[k] >= n) return SBLX_E_ARG;
+    }
+    build_topology(H);
+    TopoScratch ts;
+    std::vector<int> iso;
+    int st;
+    H.base_islands = 0;
+    H.base_islands = analyze_scenario(H, nullptr, 0, ts, iso, st);
+    std::vector<int> out;
+    for (int64_t s = 0; s < B; ++s) {
+      out.clear();
+      bool bad = false;
+      for (int q = outage_ptr[s]; q < outage_ptr[s + 1]; ++q) {
+        const int br = outage_branch[q] - index_base;
+        if (br < 0 || br >= nbranch) bad = true; else out.push_back(br);
+      }
+      std::vector<std::vector<int>> islands;
+      int cnt = 0;
+      st = SBLX_ST_BAD_BRANCH;
+      if (!bad) cnt = analyze_scenario(H, out.data(), (int)out.size(), ts, iso, st, &islands);
+      if (island_count) island_count[s] = bad ? 0 : cnt;
+      if (status) status[s] = st;
+      if (n_isolated) n_isolated[s] = bad ? 0 : (int)iso.size();
+    }
+    return SBLX_OK;
+  } catch (...) {
+    return SBLX_E_INTERNAL;
+  }
+}
+
 int sblx_analyze_only(int64_t n, const int64_t* colptr, const int64_t* rowval, int64_t slack_idx, const sblx_options* opts,
                       sblx_info* info, double* selftest_residual) {
   try {

@@ -293,6 +293,28 @@ class Engine:
         return r.value
 
 
+def topology_only(a, cases):
+    """Host-only topology verdicts of sblx_solve_outages for the outage sets `cases` (no CUDA):
+    -> (island_count, status, n_isolated); status -1 one system, -2 island-wise, 7 islanded without reference."""
+    lib = L.load()
+    ptr = np.zeros(len(cases) + 1, np.int32)
+    ptr[1:] = np.cumsum([len(c) for c in cases])
+    br = np.ascontiguousarray([k for c in cases for k in c], np.int32)
+    if br.size == 0:
+        br = np.zeros(1, np.int32)
+    isl = np.zeros(len(cases), np.int32)
+    st = np.zeros(len(cases), np.int32)
+    niso = np.zeros(len(cases), np.int32)
+    bt = np.ascontiguousarray(a.bus_type, np.uint8)
+    f = np.ascontiguousarray(a.br_from, np.int32)
+    t = np.ascontiguousarray(a.br_to, np.int32)
+    bs = np.ascontiguousarray(a.br_status, np.uint8)
+    L.check(lib.sblx_debug_topology(a.n, a.slack, L.ptr(bt, L.c_u8p), len(f), L.ptr(f, L.c_i32p), L.ptr(t, L.c_i32p), L.ptr(bs, L.c_u8p), 0,
+                                    len(cases), L.ptr(ptr, L.c_i32p), L.ptr(br, L.c_i32p), L.ptr(isl, L.c_i32p), L.ptr(st, L.c_i32p),
+                                    L.ptr(niso, L.c_i32p)), None)
+    return isl, st, niso
+
+
 def analyze_only(Y: sp.csc_matrix, slack: int, **options):
     """Symbolic analysis without CUDA (CPU tests)."""
     lib = L.load()

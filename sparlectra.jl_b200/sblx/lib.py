@@ -61,6 +61,7 @@ EXPORTS = [
     "sblx_set_v0", "sblx_get_info", "sblx_get_stats", "sblx_solve_outages", "sblx_solve_injections", "sblx_solve_one",
     "sblx_stage_outages", "sblx_run_staged", "sblx_fetch_results", "sblx_device_summary", "sblx_debug_pattern",
     "sblx_debug_newton_step", "sblx_debug_host_selftest", "sblx_analyze_only", "sblx_debug_phase_cycles",
+    "sblx_debug_topology",
 ]
 
 _lib = None
@@ -102,6 +103,8 @@ def load():
     lib.sblx_debug_host_selftest.argtypes = [vp, C.c_uint64, c_f64p]
     lib.sblx_analyze_only.argtypes = [C.c_int64, c_i64p, c_i64p, C.c_int64, C.POINTER(Options), C.POINTER(Info), c_f64p]
     lib.sblx_debug_phase_cycles.argtypes = [c_f64p]
+    lib.sblx_debug_topology.argtypes = [C.c_int64, C.c_int64, c_u8p, C.c_int64, c_i32p, c_i32p, c_u8p, C.c_int32, C.c_int64, c_i32p,
+                                        c_i32p, c_i32p, c_i32p, c_i32p]
     for name in EXPORTS:
         if getattr(lib, name).restype is C.c_int and name not in ("sblx_version",):
             getattr(lib, name).restype = C.c_int

@@ -262,3 +262,35 @@ def test_contingency_reporting_helpers(tmp_path):
     assert rows[0].startswith("name;converged;iterations")
     assert rows[1] == "B_ACL_1_2;true;4;0.98123;1.06;87.25;;Bus9;1;"
     assert rows[2].split(";")[1:6] == ["false", "30", "NaN", "NaN", "NaN"]
+
+
+def test_host_topology_analysis_matches_oracle_on_random_outage_sets():
+    """The per-scenario topology verdict of sblx_solve_outages (host code, no CUDA needed): island count, isolated
+    buses and the islanded-without-reference verdict against the oracle's restatement of markIsolatedBuses! /
+    detect_ac_islands (network.jl:1881-1930, ac_islands.jl:50-93,228-287) on thousands of random N-1..N-5 sets of
+    nearly radial grids (includes the cut-bus case the connected-grid shortcut once missed)."""
+    rng = np.random.default_rng(17)
+    total = multi = noref = 0
+    for r in range(12):
+        g = G.random_meshed_grid(int(rng.integers(15, 160)), int(rng.integers(1, 10**6)), extra_edge_frac=float(rng.uniform(0.0, 0.3)),
+                                 pv_frac=float(rng.uniform(0.05, 0.4)))
+        a = M.build_arrays(g)
+        cases = [sorted(int(x) for x in rng.choice(g.nbranch, size=int(rng.integers(1, 6)), replace=False)) for _ in range(250)]
+        isl, st, niso = api.topology_only(a, cases)
+        for i, c in enumerate(cases):
+            iso = O.mark_isolated(g, c)
+            types = O.bus_types_from_prosumers(g, iso)
+            comps = [cc for cc in O.ac_islands(g, c, iso)]
+            with_br = [cc for cc in comps if len(cc) > 1]
+            want_cnt = len(comps) if len(comps) >= 1 else 0
+            assert niso[i] == len(iso), (g.name, c)
+            has_ref = [any(types[b] in (O.SLACK, O.PV) for b in cc) for cc in with_br]
+            if len(with_br) > 1:
+                multi += 1
+                if not all(has_ref):
+                    noref += 1
+                    assert st[i] == 7, (g.name, c, st[i])
+                else:
+                    assert st[i] == -2 and isl[i] == len(with_br), (g.name, c, st[i], isl[i], len(with_br))
+            total += 1
+    assert total == 3000 and multi > 500 and noref > 100
