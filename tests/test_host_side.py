@@ -294,3 +294,20 @@ def test_host_topology_analysis_matches_oracle_on_random_outage_sets():
                     assert st[i] == -2 and isl[i] == len(with_br), (g.name, c, st[i], isl[i], len(with_br))
             total += 1
     assert total == 3000 and multi > 500 and noref > 100
+
+
+def test_symbolic_selftest_randomised_options():
+    """Host walk over the panels / index maps (the same maps the kernels use) on random grids with random symbolic
+    options: ordering, amalgamation thresholds, panel shared-memory budget."""
+    rng = np.random.default_rng(23)
+    for r in range(24):
+        if r % 2:
+            g = G.tiled_grid(rows=int(rng.integers(3, 45)), cols=int(rng.integers(3, 45)), augment=True)
+        else:
+            g = G.random_meshed_grid(int(rng.integers(10, 1200)), int(rng.integers(1, 10**6)), extra_edge_frac=float(rng.uniform(0.0, 1.2)))
+        a = M.build_arrays(g)
+        opts = dict(ordering=int(rng.integers(0, 3)), relax_small=int(rng.integers(1, 48)), relax_zero_frac=float(rng.uniform(0.0, 0.5)),
+                    panel_smem_kb=float(rng.choice([16, 24, 48, 100, 200])))
+        info, res = api.analyze_only(a.Y, a.slack, **opts)
+        assert res < 1e-9, (g.name, opts, res)
+        assert info["n_panels"] >= 1 and info["u_blocks"] >= info["m"]
