@@ -311,3 +311,30 @@ def test_symbolic_selftest_randomised_options():
         info, res = api.analyze_only(a.Y, a.slack, **opts)
         assert res < 1e-9, (g.name, opts, res)
         assert info["n_panels"] >= 1 and info["u_blocks"] >= info["m"]
+
+
+@pytest.mark.parametrize("name", ["clique", "star", "hub_behind_slack", "chain", "ring", "bipartite", "two_bus"])
+def test_symbolic_selftest_pathological_graphs(name):
+    """Dense, star-shaped, chain-like and tiny patterns through both orderings (panel chains of dense supernodes,
+    hundreds of independent leaves, level counts of the minimum-degree order on a chain)."""
+    edges, n = {
+        "clique": ([(i, j) for i in range(70) for j in range(i + 1, 70)], 70),
+        "star": ([(0, j) for j in range(1, 400)], 400),
+        "hub_behind_slack": ([(1, j) for j in range(2, 200)] + [(0, 1)], 200),
+        "chain": ([(i, i + 1) for i in range(1499)], 1500),
+        "ring": ([(i, (i + 1) % 900) for i in range(900)], 900),
+        "bipartite": ([(i, 40 + j) for i in range(40) for j in range(40)], 80),
+        "two_bus": ([(0, 1)], 2),
+    }[name]
+    r = np.array([e[0] for e in edges] + [e[1] for e in edges] + list(range(n)))
+    c = np.array([e[1] for e in edges] + [e[0] for e in edges] + list(range(n)))
+    Y = sp.csc_matrix((np.ones(len(r)) + 0j, (r, c)), shape=(n, n))
+    levels = {}
+    for o in (1, 2):
+        info, res = api.analyze_only(Y, 0, ordering=o)
+        assert res < 1e-9, (name, o, res)
+        levels[o] = info["n_levels"]
+    if name == "chain":
+        assert levels[2] < 30 < levels[1]          # nested dissection keeps a chain shallow, minimum degree does not
+        info, _ = api.analyze_only(Y, 0)           # ... and the automatic choice takes the shallow one
+        assert info["ordering"] == "nd"
