@@ -621,3 +621,33 @@ def test_locked_pv_list_in_island_wise_solves_addresses_island_numbering():
             if o.converged:
                 assert int(raw["iterations"][i]) == o.iters and np.max(np.abs(raw["V"][i] - o.V)) <= VTOL, (lock, c)
                 assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8)), (lock, c)
+
+
+@pytest.mark.parametrize("shape", ["clique", "star", "chain"])
+def test_dense_star_and_chain_topologies_parity(shape):
+    """Shapes at the edges of the symbolic code: a complete graph (one dense supernode, panel chains of 16 pivots), a
+    star (every branch outage isolates a leaf) and a long chain (deep tree; every outage splits the grid)."""
+    rng = np.random.default_rng(9)
+    n = {"clique": 36, "star": 60, "chain": 80}[shape]
+    gb = G.GridBuilder(shape, 100.0)
+    for i in range(n):
+        gb.add_bus(f"N{i + 1}")
+    if shape == "clique":
+        edges = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    elif shape == "star":
+        edges = [(0, j) for j in range(1, n)]
+    else:
+        edges = [(i, i + 1) for i in range(n - 1)]
+    for (i, j) in edges:
+        x = float(rng.uniform(0.01, 0.03)) if shape == "chain" else float(rng.uniform(0.02, 0.08))
+        gb.add_pi_line(i, j, 0.2 * x, x, float(rng.uniform(0.0, 0.005 if shape == "chain" else 0.02)), 0.0, rating=400.0)
+    for i in range(1, n):
+        p = float(rng.uniform(5.0, 30.0)) if shape == "clique" else float(rng.uniform(0.3, 1.0)) if shape == "chain" else float(rng.uniform(1.0, 4.0))
+        gb.add_prosumer(i, "ENERGYCONSUMER", p=p, q=0.3 * p)
+        if i % 9 == 4:
+            gb.add_prosumer(i, "GENERATOR", p=(8.0 if shape == "chain" else 3.0) * p, q=0.0, vm_pu=1.01, qMin=-15.0, qMax=15.0)
+    gb.add_prosumer(0, "EXTERNALNETWORKINJECTION", p=0.0, q=0.0, vm_pu=1.02, va_deg=0.0, reference=True)
+    g = gb.build()
+    cases = O.generate_n1_branches(g)[:: max(1, len(edges) // 60)] + [[0, 1], [2, len(edges) - 1]]
+    raw, oracle, _ = _run_both(g, cases)
+    _compare_batch(g, cases, raw, oracle, shape)
