@@ -651,3 +651,21 @@ def test_dense_star_and_chain_topologies_parity(shape):
     cases = O.generate_n1_branches(g)[:: max(1, len(edges) // 60)] + [[0, 1], [2, len(edges) - 1]]
     raw, oracle, _ = _run_both(g, cases)
     _compare_batch(g, cases, raw, oracle, shape)
+
+
+@pytest.mark.parametrize("slots", [1, 3, 8, 37])
+def test_slot_refill_with_few_resident_slots(slots):
+    """Continuous batching: far more scenarios than resident slots, with short (4-5 iterations), long (Q-limit
+    switching), non-convergent (30 iterations) and island-wise scenarios mixed, so slots are refilled at different
+    ticks.  Results must equal the oracle's and must not depend on the number of slots."""
+    g = G.tiled_grid(rows=9, cols=9, augment=True, pv_every=3, pv_q_mvar=14.0, rating_mva=60.0)
+    rng = np.random.default_rng(77)
+    n1 = O.generate_n1_branches(g)
+    n2 = [sorted(rng.choice(g.nbranch, size=2, replace=False).tolist()) for _ in range(40)]
+    n5 = [sorted(rng.choice(g.nbranch, size=5, replace=False).tolist()) for _ in range(25)]
+    corner = 8
+    inc = [k for k in range(g.nbranch) if g.br_from[k] == corner or g.br_to[k] == corner]
+    cases = n1 + n2 + n5 + [inc]
+    raw, oracle, stats = _run_both(g, cases, max_slots=slots)
+    _compare_batch(g, cases, raw, oracle, f"refill{slots}")
+    assert stats["ticks"] > (len(cases) // max(slots, 1)) * 3
