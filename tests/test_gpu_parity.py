@@ -669,3 +669,32 @@ def test_slot_refill_with_few_resident_slots(slots):
     raw, oracle, stats = _run_both(g, cases, max_slots=slots)
     _compare_batch(g, cases, raw, oracle, f"refill{slots}")
     assert stats["ticks"] > (len(cases) // max(slots, 1)) * 3
+
+
+def test_handles_are_independent_and_reusable():
+    """Two live handles on different grids with interleaved calls, and one handle reused for batches of very different
+    sizes and kinds (outages, injections, single solve): every call returns what a fresh handle returns."""
+    g1, g2 = G.case14(), G.tiled_grid(rows=8, cols=8, augment=True, pv_every=3, pv_q_mvar=16.0)
+    def fresh(g, cases):
+        e = api.Engine(M.build_arrays(g))
+        r = e.solve_outages(cases)
+        e.close()
+        return r
+    c1 = [[k] for k in range(g1.nbranch)]
+    c2 = [[k] for k in range(0, g2.nbranch, 3)]
+    want1, want2 = fresh(g1, c1), fresh(g2, c2)
+    e1, e2 = api.Engine(M.build_arrays(g1)), api.Engine(M.build_arrays(g2))
+    a2 = M.build_arrays(g2)
+    for rep in range(3):
+        r2 = e2.solve_outages(c2)
+        r1 = e1.solve_outages(c1)
+        small = e2.solve_outages(c2[:2])
+        inj = e2.solve_injections(np.tile(a2.s_spec, (5, 1)), None)
+        one = e2.solve_one(None)
+        for k in ("converged", "iterations", "status", "island_count"):
+            assert np.array_equal(r1[k], want1[k]) and np.array_equal(r2[k], want2[k]), (rep, k)
+            assert np.array_equal(small[k], want2[k][:2]), (rep, k)
+        assert np.array_equal(r1["V"], want1["V"]) and np.array_equal(r2["V"], want2["V"])     # bit-identical run to run
+        assert inj["converged"].all() and len(set(inj["iterations"].tolist())) == 1
+        assert one[1] and one[2] == int(inj["iterations"][0])
+    e1.close(); e2.close()
