@@ -698,3 +698,33 @@ def test_handles_are_independent_and_reusable():
         assert inj["converged"].all() and len(set(inj["iterations"].tolist())) == 1
         assert one[1] and one[2] == int(inj["iterations"][0])
     e1.close(); e2.close()
+
+
+def test_concurrent_callers_on_separate_handles():
+    """Two host threads, one handle each (the contract of include/sblx.h), solving at the same time: the results equal
+    the serial ones.  A third thread hammering ONE of the handles is serialised by the handle's mutex."""
+    import threading
+    g1, g2 = G.tiled_grid(rows=10, cols=10, augment=True), G.random_meshed_grid(200, 4)
+    jobs = []
+    for g in (g1, g2):
+        cases = [[k] for k in range(0, g.nbranch, 2)]
+        e = api.Engine(M.build_arrays(g))
+        jobs.append((e, cases, e.solve_outages(cases)))
+    out = {}
+    def work(tag, e, cases, reps):
+        res = []
+        for _ in range(reps):
+            res.append(e.solve_outages(cases))
+        out[tag] = res
+    th = [threading.Thread(target=work, args=(0, jobs[0][0], jobs[0][1], 4)),
+          threading.Thread(target=work, args=(1, jobs[1][0], jobs[1][1], 4)),
+          threading.Thread(target=work, args=(2, jobs[1][0], jobs[1][1][:7], 6))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for tag, (e, cases, want) in ((0, jobs[0]), (1, jobs[1])):
+        for r in out[tag]:
+            assert np.array_equal(r["iterations"], want["iterations"]) and np.array_equal(r["V"], want["V"])
+    for r in out[2]:
+        assert np.array_equal(r["iterations"], jobs[1][2]["iterations"][:7]) and np.array_equal(r["V"], jobs[1][2]["V"][:7])
+    for e, _, _ in jobs:
+        e.close()
