@@ -91,26 +91,29 @@ def mismatchInf(model: PFModel, V) -> float:
 # Engine: one handle = one grid on one GPU
 # ---------------------------------------------------------------------------
 class Engine:
-    def __init__(self, arrays: M.ModelArrays, **options):
+    def __init__(self, arrays: M.ModelArrays, index_base: int = 0, **options):
+        """`index_base` = what the C ABI is driven with (0, or 1 like the Julia glue: CSC colptr / rowval, slack, branch
+        terminals, outage and lock ids are shifted accordingly); the methods of this class always take 0-based ids."""
         self.lib = L.load()
         self.a = arrays
         self.n = arrays.n
-        self.opt = L.default_options(index_base=0, base_mva=arrays.baseMVA, **options)
+        self.base = int(index_base)
+        self.opt = L.default_options(index_base=self.base, base_mva=arrays.baseMVA, **options)
         Y = arrays.Y.tocsc()
         Y.sort_indices()
         self._keep = dict(
-            colptr=np.ascontiguousarray(Y.indptr, np.int64), rowval=np.ascontiguousarray(Y.indices, np.int64),
+            colptr=np.ascontiguousarray(Y.indptr + self.base, np.int64), rowval=np.ascontiguousarray(Y.indices + self.base, np.int64),
             nz=L.c128_to_f64(Y.data), bt=np.ascontiguousarray(arrays.bus_type, np.uint8),
             vset=np.ascontiguousarray(arrays.vset, float), s=L.c128_to_f64(arrays.s_spec), v0=L.c128_to_f64(arrays.v0),
             qmin=np.ascontiguousarray(arrays.qmin, float), qmax=np.ascontiguousarray(arrays.qmax, float),
-            ql=np.ascontiguousarray(arrays.qload, float), bf=np.ascontiguousarray(arrays.br_from, np.int32),
-            bt2=np.ascontiguousarray(arrays.br_to, np.int32), y11=L.c128_to_f64(arrays.y11), y12=L.c128_to_f64(arrays.y12),
+            ql=np.ascontiguousarray(arrays.qload, float), bf=np.ascontiguousarray(np.asarray(arrays.br_from) + self.base, np.int32),
+            bt2=np.ascontiguousarray(np.asarray(arrays.br_to) + self.base, np.int32), y11=L.c128_to_f64(arrays.y11), y12=L.c128_to_f64(arrays.y12),
             y21=L.c128_to_f64(arrays.y21), y22=L.c128_to_f64(arrays.y22),
             rt=np.ascontiguousarray(arrays.br_rating, float), st=np.ascontiguousarray(arrays.br_status, np.uint8))
         k = self._keep
         h = C.c_void_p()
         rc = self.lib.sblx_create(C.byref(h), self.n, L.ptr(k["colptr"], L.c_i64p), L.ptr(k["rowval"], L.c_i64p),
-                                  L.ptr(k["nz"], L.c_f64p), arrays.slack, L.ptr(k["bt"], L.c_u8p), L.ptr(k["vset"], L.c_f64p),
+                                  L.ptr(k["nz"], L.c_f64p), arrays.slack + self.base, L.ptr(k["bt"], L.c_u8p), L.ptr(k["vset"], L.c_f64p),
                                   L.ptr(k["s"], L.c_f64p), L.ptr(k["v0"], L.c_f64p), L.ptr(k["qmin"], L.c_f64p),
                                   L.ptr(k["qmax"], L.c_f64p), L.ptr(k["ql"], L.c_f64p), len(arrays.br_from),
                                   L.ptr(k["bf"], L.c_i32p), L.ptr(k["bt2"], L.c_i32p), L.ptr(k["y11"], L.c_f64p),
@@ -146,7 +149,7 @@ class Engine:
         L.check(self.lib.sblx_set_v0(self.h, L.ptr(v, L.c_f64p)), self.h)
 
     def set_locked_pv(self, buses):
-        b = np.ascontiguousarray(buses, np.int32)
+        b = np.ascontiguousarray(np.asarray(buses, np.int64) + self.base, np.int32)
         L.check(self.lib.sblx_set_locked_pv(self.h, len(b), L.ptr(b, L.c_i32p)), self.h)
 
     # -- solves -------------------------------------------------------------
@@ -190,12 +193,16 @@ class Engine:
         B = len(cases)
         optr, obr = self.pack_outages(cases) if not isinstance(cases, tuple) else cases
         B = len(optr) - 1
+        if self.base:
+            obr = np.ascontiguousarray(obr + self.base, np.int32)
         r = self._alloc(B, self.n, want_v, want_types)
         s = self._results_struct(r)
         L.check(self.lib.sblx_solve_outages(self.h, B, L.ptr(optr, L.c_i32p), L.ptr(obr, L.c_i32p), C.byref(s)), self.h)
         return r
 
     def stage_outages(self, optr, obr, want_v=False, want_types=False):
+        if self.base:
+            obr = np.ascontiguousarray(obr + self.base, np.int32)
         L.check(self.lib.sblx_stage_outages(self.h, len(optr) - 1, L.ptr(optr, L.c_i32p), L.ptr(obr, L.c_i32p),
                                             int(want_v), int(want_types)), self.h)
         self._staged = (len(optr) - 1, want_v, want_types)

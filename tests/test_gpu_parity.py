@@ -728,3 +728,25 @@ def test_concurrent_callers_on_separate_handles():
         assert np.array_equal(r["iterations"], jobs[1][2]["iterations"][:7]) and np.array_equal(r["V"], jobs[1][2]["V"][:7])
     for e, _, _ in jobs:
         e.close()
+
+
+def test_one_based_abi_gives_the_same_results():
+    """index_base = 1 is what the Julia glue drives the C ABI with (1-based CSC colptr / rowval, slack, branch
+    terminals, outage and lock ids); it must give exactly the results of the 0-based path."""
+    g = G.random_meshed_grid(180, 12, pv_q_mvar=30.0)
+    vm, va, flat, base = O.solve_base(g)
+    a = M.build_arrays(g, vm=vm, va_deg=va, flatstart=flat)
+    pv = np.flatnonzero(a.bus_type == M.BUS_PV)
+    cases = [[k] for k in range(0, g.nbranch, 3)] + [[0, 5], [g.nbranch - 1, 7], [], [g.nbranch + 3]]
+    res = []
+    for base_idx in (0, 1):
+        e = api.Engine(a, index_base=base_idx)
+        e.set_locked_pv([int(pv[0])])
+        res.append(e.solve_outages(cases))
+        e.close()
+    for k in ("converged", "status", "iterations", "island_count", "n_switch_events"):
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert np.array_equal(res[0]["V"], res[1]["V"]) and np.array_equal(res[0]["bus_type_final"], res[1]["bus_type_final"])
+    assert res[1]["status"][-1] == 8 and res[1]["converged"][-2]
+    o = O.runpf(g, vm, va, cases[1], flatstart=flat, lock=[int(pv[0])])
+    assert o.converged == bool(res[1]["converged"][1]) and o.iters == int(res[1]["iterations"][1])
