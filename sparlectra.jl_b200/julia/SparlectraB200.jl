@@ -100,7 +100,10 @@ Builds the engine from a net whose node voltages are the warm start (the solved 
 `runContingencies!`, src/contingency.jl:275-287).  Requires a net without isolated buses (the full
 n x n Ybus of `runpf_rectangular!`, rectangular_network_solver.jl:470-475).
 """
-function Engine(net::Sparlectra.Net; tol::Float64 = 1e-8, maxIte::Int = 30, vm_min_pu = 0.9, vm_max_pu = 1.1, kwargs...)
+function Engine(net::Sparlectra.Net; tol::Float64 = 1e-8, maxIte::Int = 30, vm_min_pu = 0.9, vm_max_pu = 1.1,
+                lock_pv_to_pq_buses::AbstractVector{Int} = Int[], kwargs...)
+  # remaining kwargs are sblx_options fields under the runpf! keyword names they mirror
+  # (damp, qlimits_enabled, qlimit_start_iter, guard_max_switches, ...); anything else is an error
   Sparlectra.refreshBusTypesFromProsumers!(net)
   isempty(net.isoNodes) || error("SparlectraB200.Engine: base net must not contain isolated buses")
   Y = Sparlectra.createYBUS(net = net, sparse = true)
@@ -128,7 +131,12 @@ function Engine(net::Sparlectra.Net; tol::Float64 = 1e-8, maxIte::Int = 30, vm_m
       reinterpret(Float64, y21), reinterpret(Float64, y22), rating, status, opt)
     _check(rc)
   end
-  return Engine(href[], n)
+  e = Engine(href[], n)
+  if !isempty(lock_pv_to_pq_buses)      # runpf!(...; lock_pv_to_pq_buses = [...]) (rectangular_network_solver.jl:1811)
+    lk = Vector{Int32}(lock_pv_to_pq_buses)
+    GC.@preserve lk _check(ccall((:sblx_set_locked_pv, LIBSBLX), Cint, (Ptr{Cvoid}, Int64, Ptr{Int32}), e.h, length(lk), lk), e.h)
+  end
+  return e
 end
 
 struct BatchResults
@@ -197,8 +205,7 @@ end
 # ---------------------------------------------------------------------------------------------
 # runContingencies! with the batched backend (src/contingency.jl:257-319)
 # ---------------------------------------------------------------------------------------------
-const _STATUS_TEXT = Dict(7 => "islanded without reference", 8 => "unknown branch",
-                          9 => "islanded (island-wise solve not supported by the batched backend)")
+const _STATUS_TEXT = Dict(7 => "islanded without reference", 8 => "unknown branch")
 
 function runContingenciesBatched!(net::Sparlectra.Net, cases::Vector{Sparlectra.ContingencyCase};
                                   vm_min_pu::Float64 = 0.9, vm_max_pu::Float64 = 1.1, maxIte::Int = 30, tol::Float64 = 1e-8,
