@@ -336,6 +336,7 @@ struct LaunchGroup {
   int lanes = 0;              // k_front: lanes per scenario (< nt: several scenarios share one warp)
   int wide = 0;               // k_front<64>: pivot blocks of 9..16 buses
   int reg = 0;                // k_front_reg: tiny fronts held in registers
+  mutable int pf_delta = -1;  // L2 prefetch distance in CTAs (lazily: prefetch multiplier x resident CTAs of this launch)
 };
 
 struct HostResults {
@@ -356,7 +357,8 @@ struct sblx_handle {
   HostModel H;
   std::string err;
   std::mutex mu;
-  int device = 0;
+  int device = 0, sm_count = 148;
+  double pf_mult = 1.0;       // SBLX_PF_MULT: prefetch distance in units of the resident CTA count
   cudaStream_t stream = nullptr;
   bool cuda_ready = false;
   // device model
@@ -485,7 +487,7 @@ static void upload_model(sblx_handle* h) {
     std::vector<ChildDev> cd(S.child_list.size());
     for (size_t k = 0; k < cd.size(); ++k) {
       const Panel& C = S.panels[S.child_list[k]];
-      cd[k] = ChildDev{(long long)C.c_off, C.h, (int)S.inv_ptr[k]};
+      cd[k] = ChildDev{(long long)C.c_off, C.h, (int)S.inv_ptr[k], S.kpiv[S.child_list[k]], 0};
     }
     h->d_childdev.upload(cd, s);
   }
@@ -604,6 +606,10 @@ static void upload_model(sblx_handle* h) {
   M.max_iter = o.max_iter; M.qlim_enabled = o.qlimits_enabled; M.qlim_start = o.qlimit_start_iter; M.cooldown = o.cooldown_iters;
   M.guard = o.guard_max_switches; M.freeze = o.freeze_after_repeated_switching;
   M.allow_reenable = (o.cooldown_iters > 0) || (o.q_hyst_pu > 0.0);   // rectangular_network_solver.jl:663-665
+  M.pf_mode = 0;
+  if (const char* e = getenv("SBLX_PF_MODE")) M.pf_mode = atoi(e);     // tuning probes
+  if (const char* e = getenv("SBLX_PF_MULT")) h->pf_mult = atof(e);
+  CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
 }
 
 static size_t slot_bytes(const HostModel& H) {
@@ -991,7 +997,15 @@ static void launch_front(sblx_handle* h, const LaunchGroup& g, int nstep) {
   constexpr int NG = NT / G;                       // scenarios per CTA
   const int stride = (g.smem + 15) / 16;           // double2 per scenario group
   dim3 grid((nstep + NG - 1) / NG, g.cnt);
-  k_front<NT, G, WIDE><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off, stride);
+  if (g.pf_delta < 0) {
+    g.pf_delta = 0;
+    if (h->M.pf_mode & 3) {
+      int occ = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front<NT, G, WIDE>, NT, (size_t)stride * 16 * NG));
+      g.pf_delta = std::max(1, (int)(h->pf_mult * h->sm_count * std::max(occ, 1)));
+    }
+  }
+  k_front<NT, G, WIDE><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off, stride, g.pf_delta);
 }
 template <int NT>
 static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {

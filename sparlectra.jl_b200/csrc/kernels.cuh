@@ -38,6 +38,7 @@ struct PanelDev {
 struct ChildDev {
   long long c_off;
   int hc, inv_off;
+  int kc, pad_;      // kc: leading structure entries of the child that are pivots of the parent
 };
 
 struct DevModel {
@@ -55,6 +56,7 @@ struct DevModel {
   long long u_blocks, c_blocks, l_blocks;
   double tol, damp, hyst, vm_min, vm_max, base_mva;
   int max_iter, qlim_enabled, qlim_start, cooldown, guard, freeze, allow_reenable;
+  int pf_mode;   // L2 prefetch experiment (SBLX_PF_MODE): 1 next CTA's pivot-row sources, 2 next CTA's whole child matrices, 4 own Schur sources
 };
 
 struct Slots {
@@ -105,6 +107,24 @@ __device__ __forceinline__ void ldg_blk(const double2* p, double2& r0, double2& 
 __device__ __forceinline__ void stg_blk(double2* p, double2 r0, double2 r1) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "d"(r0.x), "d"(r0.y), "d"(r1.x), "d"(r1.y) : "memory");
 }
+// One bulk L2 prefetch (UBLKPF.L2: uniform operands, so a single thread issues it); chunked, 16 B granularity.
+__device__ __forceinline__ void l2_prefetch_range(const void* p, size_t bytes) {
+  const char* c = reinterpret_cast<const char*>(p);
+  bytes = (bytes + 15) & ~(size_t)15;
+  while (bytes > 0) {
+    const unsigned n = bytes > 32768 ? 32768u : (unsigned)bytes;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(c)), "r"(n) : "memory");
+    c += n;
+    bytes -= n;
+  }
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS), no register staging
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(__cvta_generic_to_global(gmem)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ unsigned long long abs_bits(double x) { return (unsigned long long)__double_as_longlong(fabs(x)); }
 __device__ __forceinline__ double bits_double(unsigned long long b) { return __longlong_as_double((long long)b); }
@@ -598,7 +618,7 @@ template <int NT, int G = NT, bool WIDE = false>
 #define SBLX_OCC128 3
 #endif
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? SBLX_OCC128 : NT == 64 ? (WIDE ? 6 : 10) : NT == 32 ? (G < 32 ? 8 : 16) : 1))
-k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels, int group_stride) {
+k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels, int group_stride, int pf_delta) {
   static_assert(G == NT || NT == 32, "lane groups need a one-warp CTA");
   extern __shared__ double2 sm2_all[];
   constexpr int NG = NT / G;
@@ -615,6 +635,34 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
 #ifdef SBLX_PHASE_TIMING
   long long tmark_ = clock64();
 #endif
+  // L2 prefetch (one thread of the LAST warp - warp 0 owns the serial pivot chain): the update matrices this front
+  // reads were written one launch earlier by thousands of other scenarios' CTAs and are long gone from L2, so every
+  // ingest / gather load is a full HBM round trip at low occupancy.  The CTA that will follow this one on the SM
+  // (pf_delta CTAs ahead in launch order: x = scenario fastest, then the next front) gets its children's matrices
+  // pulled into L2 now with a few bulk prefetches; its loads then pay L2 latency instead of HBM latency.
+  if (G == NT && M.pf_mode != 0 && (int)threadIdx.x == (NT > 32 ? NT - 32 : 0)) {
+    if ((M.pf_mode & 3) && pf_delta > 0) {
+      const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + pf_delta;
+      const int y2 = (int)(lin / gridDim.x), x2 = (int)(lin - (long long)y2 * gridDim.x);
+      if (y2 < (int)gridDim.y && x2 < nact) {
+        const PanelDev P2 = group_panels[y2];
+        const int slot2 = L.step[x2];
+        const double* Cs2 = A.C + (size_t)slot2 * M.c_blocks * 4;
+        for (int ci = 0; ci < P2.nchild; ++ci) {
+          const ChildDev Cd = M.childdev[P2.child_ptr + ci];
+          const size_t nb = (M.pf_mode & 2) ? (size_t)Cd.hc * Cd.hc * 32 + (size_t)Cd.hc * 16 : (size_t)Cd.kc * Cd.hc * 32;
+          l2_prefetch_range(Cs2 + Cd.c_off * 4, nb);
+        }
+      }
+    }
+    if (M.pf_mode & 4) {
+      const double* Cs1 = A.C + (size_t)slot * M.c_blocks * 4;
+      for (int ci = 0; ci < P.nchild; ++ci) {
+        const ChildDev Cd = M.childdev[P.child_ptr + ci];
+        l2_prefetch_range(Cs1 + (Cd.c_off + (long long)Cd.kc * Cd.hc) * 4, (size_t)(Cd.hc - Cd.kc) * Cd.hc * 32 + (size_t)Cd.hc * 16);
+      }
+    }
+  }
   // T0/T1: pivot rows [w][nf] (block row 0 / block row 1 planes); L0/L1: structure rows x pivot columns stored
   // PIVOT-MAJOR [w][h] so that consecutive threads (consecutive structure rows) hit consecutive 16 B words.
   double2* T0 = sm2;
@@ -637,6 +685,39 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
   // IB panel blocks per thread and step: the IB index pairs are loaded first, then all value loads are in flight
   // together (single-source blocks: one dependent load level); multi-source blocks (8 %) take the CSR side path.
   constexpr int IB = SBLX_INGEST_BATCH;
+#ifdef SBLX_CPASYNC
+  // asynchronous variant: single-source blocks (92 %) go global -> shared with two 16-byte LDGSTS each, nothing is staged
+  // in registers and a thread keeps ALL its blocks in flight; multi-source blocks take the synchronous side path.
+  // The caller waits (cp.async.wait_group) before the barrier that publishes the panel.
+  auto ingest_range = [&](int lo, int hi, int t0, int tstep) {
+    for (int t = lo + t0; t < hi; t += tstep) {
+      const int2 e = ipairs[t];
+      const int v = e.x, k = e.y;
+      double2* d0 = k < nT ? T0 + k : L0 + (k - nT);
+      double2* d1 = k < nT ? T1 + k : L1 + (k - nT);
+      if (v == ING_NONE) {
+        *d0 = make_double2(0.0, 0.0);
+        *d1 = make_double2(0.0, 0.0);
+      } else if (v < ING_MULTI) {
+        const double2* ptr = v < 0 ? Jv + 2 * (size_t)(~v) : Ca + 2 * (size_t)v;
+        cp_async16(d0, ptr);
+        cp_async16(d1, ptr + 1);
+      } else {
+        const int x = v - ING_MULTI;
+        double2 x0 = make_double2(0.0, 0.0), x1 = x0;
+        for (int q = M.ing_xptr[x]; q < M.ing_xptr[x + 1]; ++q) {
+          const int sidx = M.ing_xsrc[q];
+          const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
+          double2 s0, s1;
+          ldg_blk(ptr, s0, s1);
+          x0 = cadd(x0, s0); x1 = cadd(x1, s1);
+        }
+        *d0 = x0;
+        *d1 = x1;
+      }
+    }
+  };
+#else
   auto ingest_range = [&](int lo, int hi, int t0, int tstep) {
     for (int t = lo + t0; t < hi; t += IB * tstep) {
       int2 e[IB];
@@ -668,8 +749,12 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
         if (e[i].y >= 0) store_block(e[i].y, x0[i], x1[i]);
     }
   };
+#endif
   {
     ingest_range(0, w * w, tid, G);                     // the pivot block
+#ifdef SBLX_CPASYNC
+    cp_async_commit();
+#endif
     const double2* r = A.rhs + (size_t)slot * M.m + P.first;
     const int* vptr = M.vec_ptr + P.first;
     for (int p = tid; p < w; p += G) {
@@ -687,9 +772,17 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
   // __shfl_sync for the trailing update - no shared-memory round trips on the serial chain.
   double2* Dv0 = b1 + w;
   double2* Dv1 = Dv0 + w;
+#ifdef SBLX_CPASYNC
+  // every thread (warp 0 too: the copies are asynchronous) queues its share of the rest of the panel behind the
+  // pivot block, then waits for the pivot-block group only
+  if (NT > 32) { ingest_rest(tid, NT); cp_async_commit(); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+  front_sync();
+  PHASE_MARK(0);
+#else
   front_sync();
   PHASE_MARK(0);   // ingest of the pivot block
   if (NT > 32 && tid >= 32) ingest_rest(tid - 32, NT - 32);
+#endif
   if (NT == 32 || tid < 32) {
     const int lane = tid;                        // lane within the scenario's group: shuffles below use width G
     const int bc = lane >> 1, hi = lane & 1;
@@ -757,6 +850,10 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
     PHASE_MARK(1);   // pivot-block chain (warp 0)
     if (NT == 32) ingest_rest(tid, G);
   }
+#ifdef SBLX_CPASYNC
+  cp_async_commit();
+  cp_async_wait<0>();
+#endif
   front_sync();
   PHASE_MARK(2);   // barrier after the chain: the other warps' share of the ingest
   // ---- step 2: independent substitution tasks, no barriers: U'12 columns (and the rhs) against the
