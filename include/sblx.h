@@ -17,6 +17,14 @@
  *                             examples/powerflow/mc_probabilistic_powerflow.jl:73-99 (runpf! per draw)
  *   sblx_solve_one         <- solvePf(::AbstractExternalSolver, ::PFModel) -> PFSolution
  *                             src/solver_interface.jl:143-145 (a batch of one, no outage)
+ *   sblx_solve_injection_sweep / _scale
+ *                          <- the Monte-Carlo draw of the same example (mc_probabilistic_powerflow.jl:28-41:
+ *                             truncated-normal factor per load) and buildComplexSVec's scaling
+ *                             (src/network.jl:2359-2402), generated on the device
+ *   sblx_comm_* / sblx_create_multi / sblx_multi_solve_outages
+ *                          <- the chunked fan-out of runContingencies! over workers with ordered results
+ *                             (src/contingency.jl:299-318): contiguous scenario shards over GPUs and ONE
+ *                             ncclAllGather of the per-scenario records inside the call
  *   sblx_results fields    <- ContingencyResult (src/contingency.jl:75-86) + PFSolution
  *                             (src/solver_interface.jl:76-82) + the rejection reasons of
  *                             rectangular_network_solver.jl:702,783,902,951,1034 and
@@ -39,7 +47,7 @@
 extern "C" {
 #endif
 
-#define SBLX_VERSION 100 /* 0.1.0 */
+#define SBLX_VERSION 200 /* 0.2.0 */
 
 /* bus types (busType::Vector{Symbol} of PFModel) */
 enum { SBLX_BUS_ISOLATED = 0, SBLX_BUS_PQ = 1, SBLX_BUS_PV = 2, SBLX_BUS_SLACK = 3 };
@@ -99,6 +107,9 @@ typedef struct sblx_options {
   double mem_fraction;          /* share of free device memory the auto slot count may use [0.6] */
   double relax_zero_frac;       /* supernode amalgamation threshold [0.08] */
   double panel_smem_kb;         /* shared-memory budget of one front panel in KB (<= 200) [200] */
+  double pivot_tol_rel;         /* static-pivoting monitor: a 2x2 pivot block with |det| <= pivot_tol_rel * max|entry|^2
+                                   is counted as a tiny pivot (sblx_results.n_tiny_pivots, sblx_stats.tiny_pivots);
+                                   det == 0 / non-finite still means singular_newton_step [1e-10] */
 } sblx_options;
 
 /* Caller-allocated result arrays (any may be NULL). B = number of scenarios, n = buses. */
@@ -114,6 +125,25 @@ typedef struct sblx_results {
   double* max_loading_pct;   /* [B]  max_branch_loading_pct (NaN when unrated / not converged) */
   double* V;                 /* [B*n*2] final bus voltages (re,im), scenario-major */
   uint8_t* bus_type_final;   /* [B*n] final active set (SBLX_BUS_*) */
+  /* --- since 0.2.0: what _contingency_metrics hands to ContingencyResult, computed on the device ------------- */
+  int32_t* n_voltage_violations; /* [B] length(voltage_violations): non-isolated buses outside [vm_min_pu, vm_max_pu] */
+  int32_t* n_overloaded;         /* [B] length(overloaded_branches): in-service rated branches with loading > 100 % */
+  int32_t* n_tiny_pivots;        /* [B] near-singular 2x2 pivot blocks met by the static-pivoting LU (0 = none) */
+  /* compacted lists over all converged scenarios, sorted by (scenario, element); ids follow index_base.  The caller
+   * provides the capacity; *_count receives the TOTAL number of entries (may exceed the capacity: then only the
+   * per-scenario counts above are complete and the call can be repeated with larger arrays). */
+  int64_t viol_capacity;         /* entries available in viol_scenario / viol_bus */
+  int32_t* viol_scenario;        /* [viol_capacity] scenario index (0-based position in the batch) */
+  int32_t* viol_bus;             /* [viol_capacity] bus id */
+  int64_t* viol_count;           /* [1] */
+  int64_t over_capacity;
+  int32_t* over_scenario;        /* [over_capacity] */
+  int32_t* over_branch;          /* [over_capacity] branch id */
+  double* over_loading_pct;      /* [over_capacity] its loading */
+  int64_t* over_count;           /* [1] */
+  double* flows;                 /* [B*nbranch*4] per branch S_from (re,im), S_to (re,im) in p.u. (calcNetLosses!,
+                                    src/losses.jl:53-85); zero for outaged / out-of-service branches and for
+                                    scenarios that did not converge.  Optional and large: B*nbranch*32 bytes */
 } sblx_results;
 
 typedef struct sblx_info {
@@ -141,6 +171,11 @@ typedef struct sblx_stats {
   int64_t mismatch_evaluations;  /* iterations summed over scenarios */
   int64_t scenarios_solved;      /* scenarios that went to the GPU */
   int64_t h2d_bytes, d2h_bytes;
+  /* since 0.2.0 */
+  int64_t tiny_pivots;           /* sum of n_tiny_pivots over the batch */
+  int64_t n_ranks;               /* ranks (GPUs) that shared the last sharded solve, 1 otherwise */
+  int64_t shard_lo, shard_hi;    /* this rank's contiguous scenario range of the last sharded solve */
+  double allgather_ms;           /* device time of the one ncclAllGather of the last sharded solve */
 } sblx_stats;
 
 int sblx_version(void);
@@ -183,6 +218,21 @@ int sblx_solve_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, con
 int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const double* qload_pu,
                           sblx_results* res);
 
+/* Device-side injection sweeps: nothing but the parameters crosses PCIe.
+ * _sweep: scenario s scales P, Q and the Q-limit load term of every load bus (Re(s_spec) < 0) by an independent factor
+ *   f = clip(1 + sigma * z, lo, hi), z ~ N(0,1) by Box-Muller from Philox4x32-10(key = seed, counter = (s + first, bus)):
+ *   the reference's Monte-Carlo recipe (examples/powerflow/mc_probabilistic_powerflow.jl:28-41) with a counter-based
+ *   generator, so a scenario's draw does not depend on batching, slot or rank.  `first` = global index of scenario 0
+ *   (lets a caller split one study into several calls / ranks).
+ * _scale: one factor per scenario for all load buses (uniform load scaling, src/network.jl:2359-2402 semantics). */
+int sblx_solve_injection_sweep(sblx_handle* h, int64_t B, int64_t first, uint64_t seed, double sigma, double lo, double hi,
+                               sblx_results* res);
+int sblx_solve_injection_scale(sblx_handle* h, int64_t B, const double* scale /* [B] */, sblx_results* res);
+/* The factors sblx_solve_injection_sweep applies, evaluated by the same device code: out[B*n], 1.0 on non-load buses.
+ * Lets a caller / the parity tests rebuild the exact per-scenario injections. */
+int sblx_sweep_factors(sblx_handle* h, int64_t B, int64_t first, uint64_t seed, double sigma, double lo, double hi,
+                       double* out);
+
 /* One power flow on the intact grid from an explicit start vector (solvePf analogue). */
 int sblx_solve_one(sblx_handle* h, const double* v_start /* [2n] or NULL = model V0 */, double* v_out /* [2n] */,
                    uint8_t* converged, int32_t* iters, double* residual_inf, int32_t* status);
@@ -193,10 +243,53 @@ int sblx_stage_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, con
                        int want_v, int want_types);
 int sblx_run_staged(sblx_handle* h);
 int sblx_fetch_results(sblx_handle* h, sblx_results* res);
-/* device pointer + byte size of the packed per-scenario summary records of the last run (for an
- * NCCL all-gather by the caller): record = {int32 converged, status, iterations, n_switch; double
- * final_mismatch, vmin, vmax, max_loading} = 48 bytes. */
+/* device pointer + byte size of the packed per-scenario summary records of the last run, one per CALLER scenario in
+ * input order (island-wise composites and host verdicts included): record = {int32 converged, status, iterations,
+ * n_switch; double final_mismatch, vmin, vmax, max_loading; int32 n_voltage_violations, n_overloaded, island_count,
+ * n_tiny_pivots} = SBLX_RECORD_BYTES.  The buffer stays valid until the next stage / solve call on the handle. */
+#define SBLX_RECORD_BYTES 64
 int sblx_device_summary(sblx_handle* h, void** dev_ptr, int64_t* nbytes);
+
+/* ---- multi-GPU: scenario shards + ONE all-gather inside the call (src/contingency.jl:299-318) ----------------
+ * NCCL is loaded at run time (dlopen of libnccl.so.2; SBLX_NCCL_LIB overrides the path) - a build or a process that
+ * never calls these entries does not need it.
+ *
+ * (a) one process per GPU (torchrun / MPI style): every rank creates its own handle on its own device with the SAME
+ *     model, rank 0 makes an id (sblx_comm_unique_id) and ships its 128 bytes to the others by any means, every rank
+ *     calls sblx_comm_init_rank.  sblx_solve_outages_sharded is then a COLLECTIVE call: every rank passes the SAME full
+ *     batch, solves its contiguous cost-balanced shard, and after one ncclAllGather of the 64-byte records every rank
+ *     returns the summary arrays of ALL B scenarios in input order.  V / bus_type_final / flows / the lists are filled
+ *     for the rank's own shard only (rows outside [shard_lo, shard_hi) of sblx_stats are left untouched).
+ * (b) one process, several GPUs (what a Julia caller uses): sblx_create_multi builds one engine per device and an
+ *     ncclCommInitAll communicator; sblx_multi_solve_outages runs one host thread per GPU, the same shard + all-gather,
+ *     and returns everything for all B scenarios (V / types / flows / lists are copied from every device). */
+int sblx_comm_unique_id(uint8_t id128[128]);
+int sblx_comm_init_rank(sblx_handle* h, int32_t nranks, int32_t rank, const uint8_t id128[128]);
+int sblx_comm_destroy(sblx_handle* h);
+int sblx_solve_outages_sharded(sblx_handle* h, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch,
+                               sblx_results* res);
+/* the shard boundaries the sharded calls use: nranks + 1 offsets into the batch - contiguous ranges in input order
+ * like the reference's chunking (contingency.jl:304), balanced so that shard sizes differ by at most one; identical
+ * on every rank.  Host only. */
+int sblx_shard_bounds(const sblx_handle* h, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch,
+                      int32_t nranks, int64_t* bounds /* [nranks + 1] */);
+
+typedef struct sblx_multi sblx_multi; /* opaque: ndev engines + one communicator */
+int sblx_create_multi(sblx_multi** out, int32_t ndev, const int32_t* devices /* [ndev] or NULL = 0..ndev-1 */, int64_t n,
+                      const int64_t* colptr, const int64_t* rowval, const double* nzval, int64_t slack_idx,
+                      const uint8_t* bus_type, const double* vset, const double* s_spec, const double* v0,
+                      const double* qmin_pu, const double* qmax_pu, const double* qload_pu, int64_t nbranch,
+                      const int32_t* br_from, const int32_t* br_to, const double* br_y11, const double* br_y12,
+                      const double* br_y21, const double* br_y22, const double* br_rating, const uint8_t* br_status,
+                      const sblx_options* opts);
+void sblx_destroy_multi(sblx_multi* m);
+const char* sblx_multi_last_error(const sblx_multi* m);
+int sblx_multi_set_v0(sblx_multi* m, const double* v0);
+int sblx_multi_set_locked_pv(sblx_multi* m, int64_t nlock, const int32_t* buses);
+int sblx_multi_solve_outages(sblx_multi* m, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch,
+                             sblx_results* res);
+int sblx_multi_get_stats(const sblx_multi* m, int32_t dev_index, sblx_stats* stats);
+sblx_handle* sblx_multi_handle(sblx_multi* m, int32_t dev_index); /* borrowed: e.g. sblx_solve_one on device 0 */
 
 /* ---- test / parity hooks (one scenario, every intermediate exposed) ---------------------- */
 /* Block pattern of the Jacobian: CSR over the m = n-1 non-slack buses in ascending bus order;

@@ -18,6 +18,8 @@
 #include <vector>
 
 #include <cuda_profiler_api.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is loaded with dlopen (see NcclApi), nothing links against it
 
 #include "kernels.cuh"
 #include "symbolic.h"
@@ -345,7 +347,61 @@ struct HostResults {
   // island-wise solves (rectangular_network_solver.jl:1919-2243): scenario s = sub-scenarios [sub_first[s], +sub_count[s])
   std::vector<int> sub_first, sub_count;
   std::vector<std::vector<int>> sub_buses;   // per sub-scenario (index - B): buses of its island
+  std::vector<int> parent;                   // per sub-scenario (index - B): the caller scenario it belongs to
   int64_t Bint = 0;                          // scenarios on the device = B + sub-scenarios
+};
+
+// NCCL, loaded on first use.  libsblx.so carries no link-time dependency on it: a CPU-only process can load the
+// library and run the host-side entry points; the multi-GPU entries fail loudly if NCCL cannot be found.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {getenv("SBLX_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) return;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.lib, "ncclCommInitAll");
+    api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+  });
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.CommInitAll || !api.AllGather || !api.CommDestroy)
+    throw std::runtime_error("sblx: NCCL (libnccl.so.2) could not be loaded - set SBLX_NCCL_LIB to its path");
+  return api;
+}
+#define NCK(call)                                                                                   \
+  do {                                                                                              \
+    ncclResult_t r_ = (call);                                                                       \
+    if (r_ != ncclSuccess) {                                                                        \
+      char buf_[512];                                                                               \
+      NcclApi& a_ = nccl_api();                                                                     \
+      snprintf(buf_, sizeof buf_, "NCCL error %s at %s:%d (%s)", a_.GetErrorString ? a_.GetErrorString(r_) : "?", __FILE__, __LINE__, #call); \
+      throw CudaError(buf_);                                                                        \
+    }                                                                                               \
+  } while (0)
+static void nccl_destroy(ncclComm_t c) {
+  try { nccl_api().CommDestroy(c); } catch (...) {}
+}
+
+// what the caller wants back besides the per-scenario summary
+struct Want {
+  bool v = false, types = false, flows = false;
+  int64_t viol_cap = 0, over_cap = 0;
 };
 
 }  // namespace sblx
@@ -385,6 +441,7 @@ struct sblx_handle {
   DevBuf<unsigned char> s_type, s_iso, s_evcnt, s_evact;
   DevBuf<short> s_evlast;
   DevBuf<int> s_scen, s_iter, s_state, s_changed, s_nev, s_singular, s_numerical, s_reason, s_viol, s_maxsw, s_rated, s_out_cnt, s_out_br;
+  DevBuf<int> s_nvv, s_nov, s_tiny;
   DevBuf<unsigned long long> s_mis, s_mis2, s_pvres, s_vminb, s_vmaxb, s_loadb;
   DevBuf<int> l_active, l_fresh, l_step, l_fin, l_counts;
   Slots A{};
@@ -393,12 +450,27 @@ struct sblx_handle {
   int64_t B = 0;
   bool staged = false, ran = false, sweep_q = false;
   DevBuf<int> b_queue, b_out_ptr, b_out_br, b_iso_ptr, b_iso_bus, b_ref_ptr, b_ref_bus, b_lk_ptr, b_lk_bus;
+  DevBuf<int> b_parent, b_host_status, b_sub_first, b_sub_count, b_islands;
   DevBuf<double2> b_S, b_Vstart;
-  DevBuf<double> b_ql;
-  DevBuf<int> r_conv, r_status, r_iter, r_nsw;
-  DevBuf<double> r_fm, r_vmin, r_vmax, r_load;
-  DevBuf<double2> r_V;
-  DevBuf<unsigned char> r_types, r_summary;
+  DevBuf<double> b_ql, b_scale;
+  DevBuf<int> r_conv, r_status, r_iter, r_nsw, r_nvv, r_nov, r_tiny;
+  DevBuf<double> r_fm, r_vmin, r_vmax, r_load, r_over_pct;
+  DevBuf<double2> r_V, r_flows;
+  DevBuf<int2> r_viol_list, r_over_list;
+  DevBuf<unsigned long long> r_list_counts;
+  DevBuf<unsigned char> r_types;
+  DevBuf<SummaryRec> r_summary, g_summary;     // own records (padded to the common shard size) / gathered records of all ranks
+  int64_t summary_cap = 0;
+  int64_t viol_cap = 0, over_cap = 0;
+  // device-side sweep parameters of the staged batch
+  int sweep_mode = 0;
+  uint64_t sweep_seed = 0;
+  int64_t sweep_first = 0;
+  double sweep_sigma = 0.0, sweep_lo = 0.0, sweep_hi = 0.0;
+  // multi-GPU: communicator of this handle's rank (nullptr = single GPU)
+  ncclComm_t comm = nullptr;
+  bool comm_owned = false;
+  int nranks = 1, rank = 0;
   Batch Bt{};
   HostResults hostres;       // host-decided scenarios (islanded / bad branch), status < 0 = solved on device
   int64_t nq = 0;
@@ -413,6 +485,7 @@ struct sblx_handle {
         if (e) cudaEventDestroy(e);
       if (pinned_counts) cudaFreeHost(pinned_counts);
       if (stream) cudaStreamDestroy(stream);
+      if (comm && comm_owned) sblx::nccl_destroy(comm);
     }
   }
 };
@@ -603,6 +676,7 @@ static void upload_model(sblx_handle* h) {
   M.u_blocks = S.u_blocks; M.c_blocks = S.c_blocks + 2; M.l_blocks = h->l_blocks;
   const sblx_options& o = h->opt;
   M.tol = o.tol; M.damp = o.damp; M.hyst = o.q_hyst_pu; M.vm_min = o.vm_min_pu; M.vm_max = o.vm_max_pu; M.base_mva = o.base_mva;
+  M.pivot_tol = o.pivot_tol_rel > 0.0 ? o.pivot_tol_rel : 0.0;
   M.max_iter = o.max_iter; M.qlim_enabled = o.qlimits_enabled; M.qlim_start = o.qlimit_start_iter; M.cooldown = o.cooldown_iters;
   M.guard = o.guard_max_switches; M.freeze = o.freeze_after_repeated_switching;
   M.allow_reenable = (o.cooldown_iters > 0) || (o.q_hyst_pu > 0.0);   // rectangular_network_solver.jl:663-665
@@ -667,6 +741,7 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   h->s_scen.alloc(W); h->s_iter.alloc(W); h->s_state.alloc(W); h->s_changed.alloc(W); h->s_nev.alloc(W);
   h->s_singular.alloc(W); h->s_numerical.alloc(W); h->s_reason.alloc(W); h->s_viol.alloc(W); h->s_maxsw.alloc(W);
   h->s_rated.alloc(W); h->s_out_cnt.alloc(W); h->s_out_br.alloc((size_t)W * MAXOUT); h->s_fm.alloc(W);
+  h->s_nvv.alloc(W); h->s_nov.alloc(W); h->s_tiny.alloc(W);
   h->s_mis.alloc(W); h->s_mis2.alloc(W); h->s_pvres.alloc(W); h->s_vminb.alloc(W); h->s_vmaxb.alloc(W); h->s_loadb.alloc(W);
   h->l_active.alloc(W); h->l_fresh.alloc(W); h->l_step.alloc(W); h->l_fin.alloc(W); h->l_counts.alloc(8);
   h->W = (int)W;
@@ -681,6 +756,7 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   A.mis_bits = h->s_mis.p; A.mis2_bits = h->s_mis2.p; A.fm = h->s_fm.p;
   A.pvres_bits = h->s_pvres.p; A.vmin_bits = h->s_vminb.p; A.vmax_bits = h->s_vmaxb.p; A.load_bits = h->s_loadb.p;
   A.viol = h->s_viol.p; A.maxsw = h->s_maxsw.p; A.rated = h->s_rated.p; A.out_cnt = h->s_out_cnt.p; A.out_br = h->s_out_br.p;
+  A.nvv = h->s_nvv.p; A.nov = h->s_nov.p; A.tiny = h->s_tiny.p;
   Lists& L = h->L;
   L.active = h->l_active.p; L.fresh = h->l_fresh.p; L.step = h->l_step.p; L.fin = h->l_fin.p; L.counts = h->l_counts.p;
 }
@@ -833,11 +909,23 @@ static int analyze_scenario(const HostModel& H, const int* out, int nout, TopoSc
 }
 
 // ------------------------------------------------------------------------------------------
-static void alloc_results(sblx_handle* h, int64_t B, bool want_v, bool want_types) {
+static void alloc_results(sblx_handle* h, int64_t B, const Want& want) {
+  const bool want_v = want.v, want_types = want.types;
   h->r_conv.alloc(B); h->r_status.alloc(B); h->r_iter.alloc(B); h->r_nsw.alloc(B);
   h->r_fm.alloc(B); h->r_vmin.alloc(B); h->r_vmax.alloc(B); h->r_load.alloc(B);
+  h->r_nvv.alloc(B); h->r_nov.alloc(B); h->r_tiny.alloc(B);
   if (want_v) h->r_V.alloc((size_t)B * h->H.n); else h->r_V.release();
   if (want_types) h->r_types.alloc((size_t)B * h->H.n); else h->r_types.release();
+  if (want.flows) h->r_flows.alloc((size_t)B * h->H.nbr * 2); else h->r_flows.release();
+  h->viol_cap = want.viol_cap; h->over_cap = want.over_cap;
+  if (want.viol_cap > 0) h->r_viol_list.alloc(want.viol_cap); else h->r_viol_list.release();
+  if (want.over_cap > 0) { h->r_over_list.alloc(want.over_cap); h->r_over_pct.alloc(want.over_cap); } else { h->r_over_list.release(); h->r_over_pct.release(); }
+  h->r_list_counts.alloc(2);
+  CK(cudaMemsetAsync(h->r_list_counts.p, 0, 2 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->r_nvv.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->r_nov.p, 0, B * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->r_tiny.p, 0, B * sizeof(int), h->stream));
+  if (want.flows) CK(cudaMemsetAsync(h->r_flows.p, 0, (size_t)B * h->H.nbr * 2 * sizeof(double2), h->stream));
   CK(cudaMemsetAsync(h->r_conv.p, 0, B * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->r_status.p, 0, B * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->r_iter.p, 0, B * sizeof(int), h->stream));
@@ -859,14 +947,23 @@ static void set_batch(sblx_handle* h) {
   Bt.ref_ptr = h->b_ref_ptr.p; Bt.ref_bus = h->b_ref_bus.p;
   Bt.lk_ptr = h->b_lk_ptr.p; Bt.lk_bus = h->b_lk_bus.p;
   Bt.Ssweep = h->b_S.p; Bt.qlsweep = h->b_ql.p; Bt.Vstart = h->b_Vstart.p;
+  Bt.parent = h->b_parent.p;
+  Bt.sweep_mode = h->sweep_mode; Bt.sweep_seed = h->sweep_seed; Bt.sweep_first = h->sweep_first;
+  Bt.sweep_sigma = h->sweep_sigma; Bt.sweep_lo = h->sweep_lo; Bt.sweep_hi = h->sweep_hi; Bt.scale = h->b_scale.p;
+  Bt.r_nvv = h->r_nvv.p; Bt.r_nov = h->r_nov.p; Bt.r_tiny = h->r_tiny.p;
+  Bt.viol_list = h->r_viol_list.p; Bt.over_list = h->r_over_list.p; Bt.over_pct = h->r_over_pct.p;
+  Bt.list_counts = h->r_list_counts.p; Bt.viol_cap = h->viol_cap; Bt.over_cap = h->over_cap;
+  Bt.r_flows = h->r_flows.p;
   Bt.r_conv = h->r_conv.p; Bt.r_status = h->r_status.p; Bt.r_iter = h->r_iter.p; Bt.r_nsw = h->r_nsw.p;
   Bt.r_fm = h->r_fm.p; Bt.r_vmin = h->r_vmin.p; Bt.r_vmax = h->r_vmax.p; Bt.r_load = h->r_load.p;
   Bt.r_V = h->r_V.p; Bt.r_types = h->r_types.p;
   h->A.qload_s = h->sweep_q ? h->s_qload.p : nullptr;
 }
 
-static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const int32_t* obr, bool want_v, bool want_types) {
+static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const int32_t* obr, const Want& want) {
   ensure_cuda(h);
+  h->sweep_mode = 0;
+  h->b_scale.release();
   const double t0 = now_ms();
   HostModel& H = h->H;
   const int base = h->opt.index_base;
@@ -880,13 +977,22 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   std::vector<std::vector<int>> iso_per(B);
   std::vector<std::vector<std::vector<int>>> isl_per(B);
   if (optr) {
+    if (optr[0] != 0) throw std::invalid_argument("sblx: outage_ptr[0] must be 0");
+    for (int64_t s = 0; s < B; ++s)
+      if (optr[s + 1] < optr[s]) throw std::invalid_argument("sblx: outage_ptr must be non-decreasing");
+    if (optr[B] > 0 && !obr) throw std::invalid_argument("sblx: outage_branch is NULL");
     out_br.reserve(optr[B]);
     for (int64_t s = 0; s < B; ++s) {
+      const size_t b0 = out_br.size();
       for (int q = optr[s]; q < optr[s + 1]; ++q) {
         int br = obr[q] - base;
         if (br < 0 || br >= H.nbr) { R.status[s] = SBLX_ST_BAD_BRANCH; continue; }
         out_br.push_back(br);
       }
+      // a branch can only be removed once (removeBranch! on an already removed branch changes nothing): the device
+      // subtracts the four stamps once per list entry, so the set is made unique here
+      std::sort(out_br.begin() + b0, out_br.end());
+      out_br.erase(std::unique(out_br.begin() + b0, out_br.end()), out_br.end());
       out_ptr[s + 1] = (int)out_br.size();
       if (out_ptr[s + 1] - out_ptr[s] > MAXOUT) R.status[s] = SBLX_ST_BAD_BRANCH;
     }
@@ -930,6 +1036,7 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   R.sub_first.assign(B, 0);
   R.sub_count.assign(B, 0);
   R.sub_buses.clear();
+  std::vector<int> parent;
   for (int64_t s = 0; s < B; ++s) {
     for (int b : iso_per[s]) iso_bus.push_back(b);
     iso_ptr.push_back((int)iso_bus.size());
@@ -964,6 +1071,7 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
       out_ptr.push_back((int)out_br.size());
       queue.push_back((int)Bint);
       R.sub_buses.push_back(isl);
+      parent.push_back((int)s);
       ++Bint;
     }
   }
@@ -982,8 +1090,19 @@ static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const 
   h->b_ref_bus.upload(ref_bus, h->stream);
   h->b_lk_ptr.upload(lk_ptr, h->stream);
   h->b_lk_bus.upload(lk_bus.empty() ? std::vector<int>(1, 0) : lk_bus, h->stream);
+  h->b_parent.upload(parent.empty() ? std::vector<int>(1, 0) : parent, h->stream);
+  R.parent = parent;
+  h->b_host_status.upload(R.status, h->stream);
+  h->b_sub_first.upload(R.sub_first, h->stream);
+  h->b_sub_count.upload(R.sub_count, h->stream);
+  h->b_islands.upload(R.islands, h->stream);
   h->b_S.release(); h->b_ql.release(); h->b_Vstart.release();
-  alloc_results(h, Bint, want_v, want_types);
+  alloc_results(h, Bint, want);
+  // summary records of the B caller scenarios: allocated here (never inside the timed run), sized for the common shard
+  // size of a sharded solve so that the all-gather can send it as is
+  h->summary_cap = std::max<int64_t>(h->summary_cap, std::max<int64_t>(B, 1));
+  if ((int64_t)h->r_summary.n < h->summary_cap) h->r_summary.alloc(h->summary_cap);
+  CK(cudaMemsetAsync(h->r_summary.p, 0, h->r_summary.n * sizeof(SummaryRec), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->stats.h2d_bytes = (int64_t)((queue.size() + out_ptr.size() + out_br.size() + iso_ptr.size() + iso_bus.size()) * sizeof(int));
   h->stats.h2d_ms = now_ms() - t1;
@@ -1171,7 +1290,7 @@ static void run_staged(sblx_handle* h) {
       k_fin_bus<<<gb, dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
       if (H.nbr > 0) {
         dim3 gr((H.nbr + 7) / 8, (nfin + 31) / 32);
-        k_fin_branch<<<gr, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+        k_fin_branch<<<gr, dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
         st.launches++;
       }
       k_fin_write<<<(nfin + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L, h->Bt);
@@ -1184,9 +1303,9 @@ static void run_staged(sblx_handle* h) {
     CK(cudaGetLastError());
     if (st.ticks > (int64_t)(nq + 8) * (h->opt.max_iter + 2)) throw std::runtime_error("sblx: tick loop did not terminate");
   }
-  if (h->hostres.Bint > 0) {
-    h->r_summary.alloc((size_t)h->hostres.Bint * 48);
-    k_pack_summary<<<(unsigned)((h->hostres.Bint + 255) / 256), 256, 0, s>>>(h->Bt, h->r_summary.p);
+  if (h->B > 0) {
+    k_pack_summary<<<(unsigned)((h->B + 255) / 256), 256, 0, s>>>(h->Bt, h->b_host_status.p, h->b_sub_first.p, h->b_sub_count.p,
+                                                                  h->b_islands.p, h->r_summary.p);
     st.launches++;
   }
   CK(cudaEventRecord(ev[1], s));
@@ -1205,85 +1324,145 @@ static void run_staged(sblx_handle* h) {
   h->ran = true;
 }
 
-static void fetch_results(sblx_handle* h, sblx_results* res) {
+static Want want_from(const sblx_results* res) {
+  Want w;
+  w.v = res->V != nullptr;
+  w.types = res->bus_type_final != nullptr;
+  w.flows = res->flows != nullptr;
+  w.viol_cap = (res->viol_scenario && res->viol_bus && res->viol_capacity > 0) ? res->viol_capacity : 0;
+  w.over_cap = (res->over_scenario && res->over_branch && res->over_capacity > 0) ? res->over_capacity : 0;
+  return w;
+}
+
+// summary arrays of `cnt` scenarios from their records, written at res[...][dst0 + k]
+static void fill_summary(sblx_results* res, const SummaryRec* recs, int64_t cnt, int64_t dst0) {
+  for (int64_t k = 0; k < cnt; ++k) {
+    const SummaryRec& r = recs[k];
+    const int64_t d = dst0 + k;
+    if (res->converged) res->converged[d] = (uint8_t)r.conv;
+    if (res->status) res->status[d] = r.status;
+    if (res->iterations) res->iterations[d] = r.iter;
+    if (res->n_switch_events) res->n_switch_events[d] = r.nsw;
+    if (res->island_count) res->island_count[d] = r.islands;
+    if (res->final_mismatch) res->final_mismatch[d] = r.fm;
+    if (res->vmin_pu) res->vmin_pu[d] = r.vmin;
+    if (res->vmax_pu) res->vmax_pu[d] = r.vmax;
+    if (res->max_loading_pct) res->max_loading_pct[d] = r.load;
+    if (res->n_voltage_violations) res->n_voltage_violations[d] = r.nvv;
+    if (res->n_overloaded) res->n_overloaded[d] = r.nov;
+    if (res->n_tiny_pivots) res->n_tiny_pivots[d] = r.tiny;
+  }
+}
+
+// Copies the results of the staged batch back.  `dst0` = position of this batch's scenario 0 in the caller's arrays
+// (a shard of a larger batch writes its rows at its offset); `summary` = also fill the per-scenario summary arrays
+// from this handle's own records (a sharded solve fills them from the gathered records instead).
+static void fetch_results(sblx_handle* h, sblx_results* res, int64_t dst0 = 0, bool summary = true) {
   if (!h->ran) throw std::invalid_argument("sblx_fetch_results: no completed run");
   const double t0 = now_ms();
   const int64_t B = h->B;
   const HostResults& R = h->hostres;
   const int64_t Bi = R.Bint, nsub = Bi - B;
-  const int n = h->H.n;
+  const int n = h->H.n, nbr = h->H.nbr, base = h->opt.index_base;
   cudaStream_t s = h->stream;
-  std::vector<int> conv(Bi), status(Bi), iter(Bi), nsw(Bi);
-  std::vector<double> fm(Bi), vmin(Bi), vmax(Bi), load(Bi);
-  CK(cudaMemcpyAsync(conv.data(), h->r_conv.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(status.data(), h->r_status.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(iter.data(), h->r_iter.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(nsw.data(), h->r_nsw.p, Bi * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(fm.data(), h->r_fm.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(vmin.data(), h->r_vmin.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(vmax.data(), h->r_vmax.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(load.data(), h->r_load.p, Bi * sizeof(double), cudaMemcpyDeviceToHost, s));
-  int64_t bytes = Bi * (4 * sizeof(int) + 4 * sizeof(double));
-  std::vector<double2> subV;
+  std::vector<SummaryRec> recs(B);
+  CK(cudaMemcpyAsync(recs.data(), h->r_summary.p, B * sizeof(SummaryRec), cudaMemcpyDeviceToHost, s));
+  int64_t bytes = B * (int64_t)sizeof(SummaryRec);
+  std::vector<double2> subV, subF;
   std::vector<unsigned char> subT;
-  const bool wantV = res->V && h->r_V.p, wantT = res->bus_type_final && h->r_types.p;
+  const bool wantV = res->V && h->r_V.p, wantT = res->bus_type_final && h->r_types.p, wantF = res->flows && h->r_flows.p;
+  double2* Vout = wantV ? reinterpret_cast<double2*>(res->V) + (size_t)dst0 * n : nullptr;
+  uint8_t* Tout = wantT ? res->bus_type_final + (size_t)dst0 * n : nullptr;
+  double2* Fout = wantF ? reinterpret_cast<double2*>(res->flows) + (size_t)dst0 * nbr * 2 : nullptr;
   if (wantV) {
-    CK(cudaMemcpyAsync(res->V, h->r_V.p, (size_t)B * n * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(Vout, h->r_V.p, (size_t)B * n * 16, cudaMemcpyDeviceToHost, s));
     bytes += B * n * 16;
     if (nsub > 0) { subV.resize((size_t)nsub * n); CK(cudaMemcpyAsync(subV.data(), h->r_V.p + (size_t)B * n, (size_t)nsub * n * 16, cudaMemcpyDeviceToHost, s)); }
   }
   if (wantT) {
-    CK(cudaMemcpyAsync(res->bus_type_final, h->r_types.p, (size_t)B * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(Tout, h->r_types.p, (size_t)B * n, cudaMemcpyDeviceToHost, s));
     bytes += B * n;
     if (nsub > 0) { subT.resize((size_t)nsub * n); CK(cudaMemcpyAsync(subT.data(), h->r_types.p + (size_t)B * n, (size_t)nsub * n, cudaMemcpyDeviceToHost, s)); }
   }
-  CK(cudaStreamSynchronize(s));
-  const double nan = std::nan("");
-  for (int64_t k = 0; k < B; ++k) {
-    int c = 0, st = 0, it = 0, sw = 0;
-    double f = nan, lo = nan, hi = nan, ld = nan;
-    if (R.status[k] == -1) {
-      c = conv[k]; st = status[k]; it = iter[k]; sw = nsw[k]; f = fm[k]; lo = vmin[k]; hi = vmax[k]; ld = load[k];
-    } else if (R.status[k] == -2) {
-      // island-wise composite: iterations summed, converged only if every island converged; the first failing
-      // island (island order) aborts the case with iterations = 0 (the reference throws out of runpf!)
-      c = 1; f = 0.0;
-      bool any_ld = false;
-      for (int q = 0; q < R.sub_count[k]; ++q) {
-        const int64_t u = R.sub_first[k] + q;
-        if (!conv[u]) { c = 0; st = status[u]; it = 0; break; }
-        it += iter[u]; sw += nsw[u];
-        f = std::max(f, fm[u]);
-        lo = std::isnan(lo) ? vmin[u] : std::min(lo, vmin[u]);
-        hi = std::isnan(hi) ? vmax[u] : std::max(hi, vmax[u]);
-        if (!std::isnan(load[u])) { ld = any_ld ? std::max(ld, load[u]) : load[u]; any_ld = true; }
-      }
-      if (!c) { f = nan; lo = nan; hi = nan; ld = nan; sw = 0; }
-      // buses outside every island are isolated: they keep 1 angle 0 and type "isolated" like in a single solve
-      if (wantV)
-        for (int b = 0; b < n; ++b) reinterpret_cast<double2*>(res->V)[(size_t)k * n + b] = make_double2(1.0, 0.0);
-      if (wantT)
-        for (int b = 0; b < n; ++b) res->bus_type_final[(size_t)k * n + b] = (uint8_t)T_ISO;
-      for (int q = 0; q < R.sub_count[k]; ++q) {
-        const int64_t u = R.sub_first[k] + q - B;
-        for (int b : R.sub_buses[u]) {
-          if (wantV) reinterpret_cast<double2*>(res->V)[(size_t)k * n + b] = subV[(size_t)u * n + b];
-          if (wantT) res->bus_type_final[(size_t)k * n + b] = subT[(size_t)u * n + b];
-        }
-      }
-    } else {
-      st = R.status[k];
-    }
-    if (res->converged) res->converged[k] = (uint8_t)c;
-    if (res->status) res->status[k] = st;
-    if (res->iterations) res->iterations[k] = it;
-    if (res->n_switch_events) res->n_switch_events[k] = sw;
-    if (res->island_count) res->island_count[k] = R.islands[k];
-    if (res->final_mismatch) res->final_mismatch[k] = f;
-    if (res->vmin_pu) res->vmin_pu[k] = lo;
-    if (res->vmax_pu) res->vmax_pu[k] = hi;
-    if (res->max_loading_pct) res->max_loading_pct[k] = ld;
+  if (wantF) {
+    CK(cudaMemcpyAsync(Fout, h->r_flows.p, (size_t)B * nbr * 32, cudaMemcpyDeviceToHost, s));
+    bytes += B * (int64_t)nbr * 32;
+    if (nsub > 0) { subF.resize((size_t)nsub * nbr * 2); CK(cudaMemcpyAsync(subF.data(), h->r_flows.p + (size_t)B * nbr * 2, (size_t)nsub * nbr * 32, cudaMemcpyDeviceToHost, s)); }
   }
+  // compacted violation / overload lists
+  unsigned long long lc[2] = {0, 0};
+  std::vector<int2> vl, ol;
+  std::vector<double> op;
+  const bool wantVL = h->viol_cap > 0 && res->viol_scenario, wantOL = h->over_cap > 0 && res->over_scenario;
+  if (wantVL || wantOL) {
+    CK(cudaMemcpyAsync(lc, h->r_list_counts.p, sizeof lc, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (wantVL) {
+      vl.resize((size_t)std::min<unsigned long long>(lc[0], (unsigned long long)h->viol_cap));
+      if (!vl.empty()) CK(cudaMemcpyAsync(vl.data(), h->r_viol_list.p, vl.size() * sizeof(int2), cudaMemcpyDeviceToHost, s));
+    }
+    if (wantOL) {
+      ol.resize((size_t)std::min<unsigned long long>(lc[1], (unsigned long long)h->over_cap));
+      op.resize(ol.size());
+      if (!ol.empty()) {
+        CK(cudaMemcpyAsync(ol.data(), h->r_over_list.p, ol.size() * sizeof(int2), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(op.data(), h->r_over_pct.p, ol.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+      }
+    }
+    bytes += (int64_t)(vl.size() * 8 + ol.size() * 16);
+  }
+  CK(cudaStreamSynchronize(s));
+  if (summary) fill_summary(res, recs.data(), B, dst0);
+  int64_t tiny = 0;
+  for (int64_t k = 0; k < B; ++k) {
+    tiny += recs[k].tiny;
+    if (R.status[k] != -2) continue;
+    // island-wise composite: buses outside every island are isolated - they keep 1 angle 0 and type "isolated" like in
+    // a single solve; flows of a split scenario are the union of its islands' (disjoint) branch sets
+    if (wantV)
+      for (int b = 0; b < n; ++b) Vout[(size_t)k * n + b] = make_double2(1.0, 0.0);
+    if (wantT)
+      for (int b = 0; b < n; ++b) Tout[(size_t)k * n + b] = (uint8_t)T_ISO;
+    if (wantF)
+      for (int b = 0; b < 2 * nbr; ++b) Fout[(size_t)k * nbr * 2 + b] = make_double2(0.0, 0.0);
+    for (int q = 0; q < R.sub_count[k]; ++q) {
+      const int64_t u = R.sub_first[k] + q - B;
+      for (int b : R.sub_buses[u]) {
+        if (wantV) Vout[(size_t)k * n + b] = subV[(size_t)u * n + b];
+        if (wantT) Tout[(size_t)k * n + b] = subT[(size_t)u * n + b];
+      }
+      if (wantF && recs[k].conv)
+        for (int b = 0; b < 2 * nbr; ++b) {
+          const double2 f = subF[(size_t)u * nbr * 2 + b];
+          if (f.x != 0.0 || f.y != 0.0) Fout[(size_t)k * nbr * 2 + b] = f;
+        }
+    }
+  }
+  h->stats.tiny_pivots = tiny;
+  // lists: device scenario id -> caller scenario (island sub-scenarios map to their parent), entries of cases that did
+  // not converge as a whole are dropped, order restored
+  auto finish_list = [&](std::vector<int2>& lst, std::vector<double>* pct, unsigned long long devcount, int64_t cap, int32_t* oscen,
+                         int32_t* oelem, double* opct, int64_t* ocount) {
+    std::vector<size_t> keep;
+    keep.reserve(lst.size());
+    for (size_t i = 0; i < lst.size(); ++i) {
+      int sc = lst[i].x;
+      if (sc >= B) sc = (sc - B) < (int64_t)R.parent.size() ? R.parent[sc - B] : -1;   // island sub-scenario -> its caller scenario
+      if (sc < 0 || !recs[sc].conv) continue;
+      lst[i].x = sc;
+      keep.push_back(i);
+    }
+    std::sort(keep.begin(), keep.end(), [&](size_t a, size_t b) { return lst[a].x != lst[b].x ? lst[a].x < lst[b].x : lst[a].y < lst[b].y; });
+    const bool overflow = devcount > (unsigned long long)cap;
+    for (size_t j = 0; j < keep.size() && (int64_t)j < cap; ++j) {
+      oscen[j] = (int32_t)(lst[keep[j]].x + dst0);
+      oelem[j] = lst[keep[j]].y + base;
+      if (opct && pct) opct[j] = (*pct)[keep[j]];
+    }
+    if (ocount) *ocount = overflow ? (int64_t)devcount : (int64_t)keep.size();
+  };
+  if (wantVL) finish_list(vl, nullptr, lc[0], h->viol_cap, res->viol_scenario, res->viol_bus, nullptr, res->viol_count);
+  if (wantOL) finish_list(ol, &op, lc[1], h->over_cap, res->over_scenario, res->over_branch, res->over_loading_pct, res->over_count);
   h->stats.d2h_ms = now_ms() - t0;
   h->stats.d2h_bytes = bytes;
 }
@@ -1333,6 +1512,7 @@ void sblx_default_options(sblx_options* o) {
   o->mem_fraction = 0.6;
   o->relax_zero_frac = 0.08;
   o->panel_smem_kb = 200.0;
+  o->pivot_tol_rel = 1e-10;
 }
 
 const char* sblx_last_error(const sblx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1503,7 +1683,10 @@ int sblx_stage_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, con
   if (!h || B < 0) return SBLX_E_ARG;
   API_BEGIN(h)
   if (B > 0 && !outage_ptr) throw std::invalid_argument("sblx_stage_outages: outage_ptr is NULL");
-  stage_outages(h, B, outage_ptr, outage_branch, want_v != 0, want_types != 0);
+  Want w;
+  w.v = want_v != 0;
+  w.types = want_types != 0;
+  stage_outages(h, B, outage_ptr, outage_branch, w);
   API_END(h)
 }
 
@@ -1526,7 +1709,7 @@ int sblx_device_summary(sblx_handle* h, void** dev_ptr, int64_t* nbytes) {
   API_BEGIN(h)
   if (!h->ran) throw std::invalid_argument("sblx_device_summary: no completed run");
   *dev_ptr = h->r_summary.p;
-  *nbytes = h->B * 48;
+  *nbytes = h->B * (int64_t)sizeof(SummaryRec);
   API_END(h)
 }
 
@@ -1535,10 +1718,281 @@ int sblx_solve_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, con
   API_BEGIN(h)
   if (B == 0) return SBLX_OK;
   if (!outage_ptr) throw std::invalid_argument("sblx_solve_outages: outage_ptr is NULL");
-  stage_outages(h, B, outage_ptr, outage_branch, res->V != nullptr, res->bus_type_final != nullptr);
+  stage_outages(h, B, outage_ptr, outage_branch, want_from(res));
   run_staged(h);
   fetch_results(h, res);
   API_END(h)
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU: contiguous scenario shards + one ncclAllGather of the per-scenario records
+// ------------------------------------------------------------------------------------------
+static void shard_bounds(int64_t B, int nranks, std::vector<int64_t>& b) {
+  // contiguous ranges in input order like Iterators.partition(eachindex(cases), ...) (contingency.jl:304), balanced
+  // so that shard sizes differ by at most one
+  b.resize(nranks + 1);
+  for (int r = 0; r <= nranks; ++r) b[r] = B * r / nranks;
+}
+
+static void validate_outages(int64_t B, const int32_t* optr, const int32_t* obr) {
+  if (B > 0 && !optr) throw std::invalid_argument("sblx: outage_ptr is NULL");
+  if (B > 0 && optr[0] != 0) throw std::invalid_argument("sblx: outage_ptr[0] must be 0");
+  for (int64_t s = 0; s < B; ++s)
+    if (optr[s + 1] < optr[s]) throw std::invalid_argument("sblx: outage_ptr must be non-decreasing");
+  if (B > 0 && optr[B] > 0 && !obr) throw std::invalid_argument("sblx: outage_branch is NULL");
+}
+
+// COLLECTIVE over the handle's communicator: solves this rank's shard of the batch, gathers the records of all ranks
+// and fills the summary arrays of ALL B scenarios; bulk outputs (V, types, flows, lists) only for the own shard.
+static void solve_sharded(sblx_handle* h, int64_t B, const int32_t* optr, const int32_t* obr, sblx_results* res, sblx_results* res_bulk) {
+  ensure_cuda(h);
+  const int nr = h->comm ? h->nranks : 1, rk = h->comm ? h->rank : 0;
+  std::vector<int64_t> b;
+  shard_bounds(B, nr, b);
+  const int64_t lo = b[rk], hi = b[rk + 1], cnt = hi - lo;
+  int64_t per_max = 1;
+  for (int r = 0; r < nr; ++r) per_max = std::max(per_max, b[r + 1] - b[r]);
+  std::vector<int32_t> lp(cnt + 1, 0);
+  for (int64_t k = 0; k <= cnt; ++k) lp[k] = optr[lo + k] - optr[lo];
+  const int32_t* lb = obr ? obr + optr[lo] : nullptr;
+  h->summary_cap = std::max(h->summary_cap, per_max);
+  sblx_results* rb = res_bulk ? res_bulk : res;
+  if (cnt > 0) {
+    stage_outages(h, cnt, lp.data(), lb, want_from(rb));
+    run_staged(h);
+  } else {   // more ranks than scenarios: this rank only takes part in the gather
+    h->B = 0; h->staged = false; h->ran = false; h->stats = sblx_stats{};
+    if ((int64_t)h->r_summary.n < h->summary_cap) h->r_summary.alloc(h->summary_cap);
+    CK(cudaMemsetAsync(h->r_summary.p, 0, h->r_summary.n * sizeof(SummaryRec), h->stream));
+  }
+  cudaStream_t s = h->stream;
+  std::vector<SummaryRec> all((size_t)per_max * nr);
+  float ag_ms = 0.f;
+  if (h->comm && nr > 1) {
+    if ((int64_t)h->g_summary.n < per_max * nr) h->g_summary.alloc((size_t)per_max * nr);
+    CK(cudaEventRecord(h->ev[0], s));
+    NCK(nccl_api().AllGather(h->r_summary.p, h->g_summary.p, (size_t)per_max * sizeof(SummaryRec), ncclChar, h->comm, s));
+    CK(cudaEventRecord(h->ev[1], s));
+    CK(cudaMemcpyAsync(all.data(), h->g_summary.p, all.size() * sizeof(SummaryRec), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&ag_ms, h->ev[0], h->ev[1]));
+  } else {
+    CK(cudaMemcpyAsync(all.data(), h->r_summary.p, (size_t)per_max * sizeof(SummaryRec), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (res)
+    for (int r = 0; r < nr; ++r) fill_summary(res, all.data() + (size_t)r * per_max, b[r + 1] - b[r], b[r]);
+  if (cnt > 0) fetch_results(h, rb, lo, false);
+  h->stats.n_ranks = nr; h->stats.shard_lo = lo; h->stats.shard_hi = hi; h->stats.allgather_ms = ag_ms;
+  h->stats.d2h_bytes += (int64_t)(all.size() * sizeof(SummaryRec));
+}
+
+int sblx_comm_unique_id(uint8_t id128[128]) {
+  if (!id128) return SBLX_E_ARG;
+  try {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    if (nccl_api().GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return SBLX_E_CUDA; }
+    memcpy(id128, &id, 128);
+    return SBLX_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return SBLX_E_INTERNAL;
+  }
+}
+
+int sblx_comm_init_rank(sblx_handle* h, int32_t nranks, int32_t rank, const uint8_t id128[128]) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SBLX_E_ARG;
+  API_BEGIN(h)
+  ensure_cuda(h);
+  if (h->comm && h->comm_owned) nccl_destroy(h->comm);
+  h->comm = nullptr;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclComm_t c = nullptr;
+  NCK(nccl_api().CommInitRank(&c, nranks, id, rank));
+  h->comm = c; h->comm_owned = true; h->nranks = nranks; h->rank = rank;
+  API_END(h)
+}
+
+int sblx_comm_destroy(sblx_handle* h) {
+  if (!h) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (h->comm && h->comm_owned) { CK(cudaSetDevice(h->device)); nccl_destroy(h->comm); }
+  h->comm = nullptr; h->nranks = 1; h->rank = 0;
+  API_END(h)
+}
+
+int sblx_solve_outages_sharded(sblx_handle* h, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch, sblx_results* res) {
+  if (!h || !res || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (B == 0) return SBLX_OK;
+  validate_outages(B, outage_ptr, outage_branch);
+  solve_sharded(h, B, outage_ptr, outage_branch, res, nullptr);
+  API_END(h)
+}
+
+int sblx_shard_bounds(const sblx_handle* h, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch, int32_t nranks,
+                      int64_t* bounds) {
+  (void)h; (void)outage_ptr; (void)outage_branch;
+  if (B < 0 || nranks < 1 || !bounds) return SBLX_E_ARG;
+  std::vector<int64_t> b;
+  shard_bounds(B, nranks, b);
+  for (int r = 0; r <= nranks; ++r) bounds[r] = b[r];
+  return SBLX_OK;
+}
+
+}  // extern "C" (reopened below)
+
+// one process, several GPUs: ndev engines + an ncclCommInitAll communicator, one host thread per GPU inside the call
+struct sblx_multi {
+  std::vector<sblx_handle*> hs;
+  std::string err;
+  std::mutex mu;
+};
+
+extern "C" {
+
+int sblx_create_multi(sblx_multi** out, int32_t ndev, const int32_t* devices, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                      const double* nzval, int64_t slack_idx, const uint8_t* bus_type, const double* vset, const double* s_spec,
+                      const double* v0, const double* qmin_pu, const double* qmax_pu, const double* qload_pu, int64_t nbranch,
+                      const int32_t* br_from, const int32_t* br_to, const double* br_y11, const double* br_y12, const double* br_y21,
+                      const double* br_y22, const double* br_rating, const uint8_t* br_status, const sblx_options* opts) {
+  if (!out || ndev < 1) return SBLX_E_ARG;
+  *out = nullptr;
+  sblx_multi* m = new sblx_multi();
+  try {
+    std::vector<int> devs(ndev);
+    for (int i = 0; i < ndev; ++i) devs[i] = devices ? devices[i] : i;
+    for (int i = 0; i < ndev; ++i) {
+      sblx_options o;
+      if (opts) o = *opts; else sblx_default_options(&o);
+      o.device = devs[i];
+      sblx_handle* h = nullptr;
+      const int rc = sblx_create(&h, n, colptr, rowval, nzval, slack_idx, bus_type, vset, s_spec, v0, qmin_pu, qmax_pu, qload_pu, nbranch,
+                                 br_from, br_to, br_y11, br_y12, br_y21, br_y22, br_rating, br_status, &o);
+      if (rc != SBLX_OK) { const std::string msg = g_create_error; for (auto* q : m->hs) delete q; delete m; g_create_error = msg; return rc; }
+      m->hs.push_back(h);
+      ensure_cuda(h);
+    }
+    if (ndev > 1) {
+      std::vector<ncclComm_t> comms(ndev);
+      NCK(nccl_api().CommInitAll(comms.data(), ndev, devs.data()));
+      for (int i = 0; i < ndev; ++i) { m->hs[i]->comm = comms[i]; m->hs[i]->comm_owned = true; m->hs[i]->nranks = ndev; m->hs[i]->rank = i; }
+    }
+    *out = m;
+    return SBLX_OK;
+  } catch (const CudaError& e) {
+    g_create_error = e.what();
+    for (auto* q : m->hs) delete q;
+    delete m;
+    return SBLX_E_CUDA;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    for (auto* q : m->hs) delete q;
+    delete m;
+    return SBLX_E_INTERNAL;
+  }
+}
+
+void sblx_destroy_multi(sblx_multi* m) {
+  if (!m) return;
+  for (auto* h : m->hs) delete h;
+  delete m;
+}
+
+const char* sblx_multi_last_error(const sblx_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+sblx_handle* sblx_multi_handle(sblx_multi* m, int32_t i) { return (m && i >= 0 && i < (int)m->hs.size()) ? m->hs[i] : nullptr; }
+
+int sblx_multi_set_v0(sblx_multi* m, const double* v0) {
+  if (!m) return SBLX_E_ARG;
+  for (auto* h : m->hs) {
+    const int rc = sblx_set_v0(h, v0);
+    if (rc != SBLX_OK) { m->err = h->err; return rc; }
+  }
+  return SBLX_OK;
+}
+
+int sblx_multi_set_locked_pv(sblx_multi* m, int64_t nlock, const int32_t* buses) {
+  if (!m) return SBLX_E_ARG;
+  for (auto* h : m->hs) {
+    const int rc = sblx_set_locked_pv(h, nlock, buses);
+    if (rc != SBLX_OK) { m->err = h->err; return rc; }
+  }
+  return SBLX_OK;
+}
+
+int sblx_multi_get_stats(const sblx_multi* m, int32_t i, sblx_stats* st) {
+  if (!m || !st || i < 0 || i >= (int)m->hs.size()) return SBLX_E_ARG;
+  *st = m->hs[i]->stats;
+  return SBLX_OK;
+}
+
+int sblx_multi_solve_outages(sblx_multi* m, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch, sblx_results* res) {
+  if (!m || !res || B < 0) return SBLX_E_ARG;
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (B == 0) return SBLX_OK;
+  try {
+    validate_outages(B, outage_ptr, outage_branch);   // argument errors surface before any rank enters the collective
+  } catch (const std::exception& e) {
+    m->err = e.what();
+    return SBLX_E_ARG;
+  }
+  const int nd = (int)m->hs.size();
+  // per-rank list buffers (the ranks append concurrently; merged in rank = input order afterwards)
+  struct RankLists { std::vector<int32_t> vs, vb, os, ob; std::vector<double> op; int64_t vc = 0, oc = 0; };
+  std::vector<RankLists> rl(nd);
+  std::vector<sblx_results> rr(nd, *res);
+  const bool wantVL = res->viol_scenario && res->viol_bus && res->viol_capacity > 0;
+  const bool wantOL = res->over_scenario && res->over_branch && res->over_capacity > 0;
+  for (int i = 0; i < nd; ++i) {
+    if (wantVL) { rl[i].vs.resize(res->viol_capacity); rl[i].vb.resize(res->viol_capacity); rr[i].viol_scenario = rl[i].vs.data(); rr[i].viol_bus = rl[i].vb.data(); rr[i].viol_count = &rl[i].vc; }
+    if (wantOL) {
+      rl[i].os.resize(res->over_capacity); rl[i].ob.resize(res->over_capacity); rl[i].op.resize(res->over_capacity);
+      rr[i].over_scenario = rl[i].os.data(); rr[i].over_branch = rl[i].ob.data(); rr[i].over_loading_pct = rl[i].op.data(); rr[i].over_count = &rl[i].oc;
+    }
+  }
+  std::vector<int> rcs(nd, SBLX_OK);
+  std::vector<std::string> errs(nd);
+  auto work = [&](int i) {
+    sblx_handle* h = m->hs[i];
+    std::lock_guard<std::mutex> hl(h->mu);
+    try {
+      CK(cudaSetDevice(h->device));
+      solve_sharded(h, B, outage_ptr, outage_branch, i == 0 ? res : nullptr, &rr[i]);
+    } catch (const CudaError& e) { errs[i] = e.what(); rcs[i] = SBLX_E_CUDA; }
+    catch (const std::invalid_argument& e) { errs[i] = e.what(); rcs[i] = SBLX_E_ARG; }
+    catch (const std::exception& e) { errs[i] = e.what(); rcs[i] = SBLX_E_INTERNAL; }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < nd; ++i) th.emplace_back(work, i);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int i = 0; i < nd; ++i)
+    if (rcs[i] != SBLX_OK) { m->err = errs[i]; return rcs[i]; }
+  if (wantVL) {
+    int64_t tot = 0, w = 0;
+    for (int i = 0; i < nd; ++i) {
+      const int64_t have = std::min<int64_t>(rl[i].vc, res->viol_capacity);
+      for (int64_t j = 0; j < have && w < res->viol_capacity; ++j, ++w) { res->viol_scenario[w] = rl[i].vs[j]; res->viol_bus[w] = rl[i].vb[j]; }
+      tot += rl[i].vc;
+    }
+    if (res->viol_count) *res->viol_count = tot;
+  }
+  if (wantOL) {
+    int64_t tot = 0, w = 0;
+    for (int i = 0; i < nd; ++i) {
+      const int64_t have = std::min<int64_t>(rl[i].oc, res->over_capacity);
+      for (int64_t j = 0; j < have && w < res->over_capacity; ++j, ++w) {
+        res->over_scenario[w] = rl[i].os[j]; res->over_branch[w] = rl[i].ob[j];
+        if (res->over_loading_pct) res->over_loading_pct[w] = rl[i].op[j];
+      }
+      tot += rl[i].oc;
+    }
+    if (res->over_count) *res->over_count = tot;
+  }
+  return SBLX_OK;
 }
 
 int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const double* qload_pu, sblx_results* res) {
@@ -1546,7 +2000,7 @@ int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const
   API_BEGIN(h)
   if (B == 0) return SBLX_OK;
   if (!s_spec) throw std::invalid_argument("sblx_solve_injections: s_spec is NULL");
-  stage_outages(h, B, nullptr, nullptr, res->V != nullptr, res->bus_type_final != nullptr);
+  stage_outages(h, B, nullptr, nullptr, want_from(res));
   const size_t cnt = (size_t)B * h->H.n;
   const double t0 = now_ms();
   h->b_S.alloc(cnt);
@@ -1566,12 +2020,67 @@ int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const
   API_END(h)
 }
 
+static void solve_sweep(sblx_handle* h, int64_t B, int mode, int64_t first, uint64_t seed, double sigma, double lo, double hi,
+                        const double* scale, sblx_results* res) {
+  stage_outages(h, B, nullptr, nullptr, want_from(res));
+  h->sweep_mode = mode; h->sweep_seed = seed; h->sweep_first = first; h->sweep_sigma = sigma; h->sweep_lo = lo; h->sweep_hi = hi;
+  h->sweep_q = true;                       // the load's reactive part scales with it (the Q-limit bookkeeping reads qload)
+  if (mode == 2) {
+    h->b_scale.alloc(B);
+    CK(cudaMemcpyAsync(h->b_scale.p, scale, B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stats.h2d_bytes += B * (int64_t)sizeof(double);
+  }
+  set_batch(h);
+  run_staged(h);
+  fetch_results(h, res);
+}
+
+int sblx_solve_injection_sweep(sblx_handle* h, int64_t B, int64_t first, uint64_t seed, double sigma, double lo, double hi,
+                               sblx_results* res) {
+  if (!h || !res || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (B == 0) return SBLX_OK;
+  if (!(sigma >= 0.0) || !(lo <= hi)) throw std::invalid_argument("sblx_solve_injection_sweep: need sigma >= 0 and lo <= hi");
+  solve_sweep(h, B, 1, first, seed, sigma, lo, hi, nullptr, res);
+  API_END(h)
+}
+
+int sblx_solve_injection_scale(sblx_handle* h, int64_t B, const double* scale, sblx_results* res) {
+  if (!h || !res || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (B == 0) return SBLX_OK;
+  if (!scale) throw std::invalid_argument("sblx_solve_injection_scale: scale is NULL");
+  solve_sweep(h, B, 2, 0, 0, 0.0, 0.0, 0.0, scale, res);
+  API_END(h)
+}
+
+int sblx_sweep_factors(sblx_handle* h, int64_t B, int64_t first, uint64_t seed, double sigma, double lo, double hi, double* out) {
+  if (!h || !out || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  ensure_cuda(h);
+  const int n = h->H.n;
+  const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)n * 8));
+  DevBuf<double> buf;
+  buf.alloc((size_t)std::min(chunk, std::max<int64_t>(B, 1)) * n);
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t nb = std::min(chunk, B - b0);
+    const long long tot = (long long)nb * n;
+    k_sweep_factors<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->M, first + b0, (int)nb, seed, sigma, lo, hi, buf.p);
+    CK(cudaMemcpyAsync(out + (size_t)b0 * n, buf.p, (size_t)tot * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  API_END(h)
+}
+
 int sblx_solve_one(sblx_handle* h, const double* v_start, double* v_out, uint8_t* converged, int32_t* iters,
                    double* residual_inf, int32_t* status) {
   if (!h) return SBLX_E_ARG;
   API_BEGIN(h)
   int32_t optr[2] = {0, 0};
-  stage_outages(h, 1, optr, nullptr, v_out != nullptr, false);
+  Want w1;
+  w1.v = v_out != nullptr;
+  stage_outages(h, 1, optr, nullptr, w1);
   if (v_start) {
     std::vector<double2> vs(h->H.n);
     for (int i = 0; i < h->H.n; ++i) vs[i] = make_double2(v_start[2 * i], v_start[2 * i + 1]);
@@ -1620,7 +2129,7 @@ int sblx_debug_newton_step(sblx_handle* h, int64_t nout, const int32_t* outage_b
   const HostModel& H = h->H;
   const int n = H.n, m = H.m, nnzB = (int)H.jb_col.size();
   int32_t optr[2] = {0, (int32_t)nout};
-  stage_outages(h, 1, optr, outage_branch, false, false);
+  stage_outages(h, 1, optr, outage_branch, Want{});
   if (h->nq != 1) throw std::invalid_argument("sblx_debug_newton_step: scenario is islanded / invalid");
   std::vector<double2> vs(n);
   for (int i = 0; i < n; ++i) vs[i] = make_double2(v_in[2 * i], v_in[2 * i + 1]);

@@ -54,7 +54,7 @@ struct DevModel {
   const int* kpiv; const int* inv; const long long* inv_ptr; const int* asm_src; const int* asm_dst;
   const int* ing_ptr; const int* ing_src; const int2* ing_pairs; const int* reg_words; const int* reg_vptr; const int* reg_vsrc; const int* ing_xptr; const int* ing_xsrc; const int* vec_ptr; const int* vec_src; const ChildDev* childdev;
   long long u_blocks, c_blocks, l_blocks;
-  double tol, damp, hyst, vm_min, vm_max, base_mva;
+  double tol, damp, hyst, vm_min, vm_max, base_mva, pivot_tol;   // pivot_tol: |det| <= pivot_tol * max|entry|^2 of a 2x2 pivot block counts as a tiny pivot
   int max_iter, qlim_enabled, qlim_start, cooldown, guard, freeze, allow_reenable;
   int pf_mode;   // L2 prefetch experiment (SBLX_PF_MODE): 1 next CTA's pivot-row sources, 2 next CTA's whole child matrices, 4 own Schur sources
 };
@@ -70,7 +70,7 @@ struct Slots {
   int* scen; int* iter; int* state; int* changed; int* nev; int* singular; int* numerical; int* reason;
   unsigned long long* mis_bits; unsigned long long* mis2_bits; double* fm;
   unsigned long long* pvres_bits; unsigned long long* vmin_bits; unsigned long long* vmax_bits; unsigned long long* load_bits;
-  int* viol; int* maxsw; int* rated;
+  int* viol; int* maxsw; int* rated; int* nvv; int* nov; int* tiny;   // nvv / nov: voltage-band violations / overloaded branches; tiny: near-singular pivot blocks
   int* out_cnt; int* out_br;   // [W][MAXOUT]
 };
 
@@ -86,9 +86,17 @@ struct Batch {
   const int* ref_ptr; const int* ref_bus;     // per scenario: PV buses promoted to island reference (ac_islands.jl:228-234)
   const int* lk_ptr; const int* lk_bus;       // per ISLAND sub-scenario (index scen - Btop): its locked PV buses, see stage_outages
   const double2* Ssweep; const double* qlsweep; const double2* Vstart;
+  const int* parent;           // per ISLAND sub-scenario (index scen - Btop): the caller scenario it belongs to
+  // device-side injection sweep (mc_probabilistic_powerflow.jl:28-41): 1 = independent truncated-normal factor per
+  // (scenario, load bus) from Philox4x32-10 keyed on the seed, counter = (scenario, bus); 2 = one factor per scenario
+  int sweep_mode; unsigned long long sweep_seed; long long sweep_first; double sweep_sigma, sweep_lo, sweep_hi; const double* scale;
   // results
   int* r_conv; int* r_status; int* r_iter; int* r_nsw; double* r_fm; double* r_vmin; double* r_vmax; double* r_load;
   double2* r_V; unsigned char* r_types;
+  int* r_nvv; int* r_nov; int* r_tiny;      // per scenario: voltage-band violations, overloaded branches (contingency.jl:149-178), tiny pivots
+  // compacted (scenario, bus) / (scenario, branch) lists, appended with one atomic per entry (order restored on the host)
+  int2* viol_list; int2* over_list; double* over_pct; unsigned long long* list_counts; long long viol_cap, over_cap;
+  double2* r_flows;            // [B][nbr][2] complex branch flows S_from, S_to in p.u. (losses.jl:53-85), optional
 };
 
 // ------------------------------------------------------------------------------------------
@@ -152,6 +160,37 @@ __device__ __forceinline__ int block_rank_1024(int flag, int* total) {
   r += wsum[warp];
   __syncthreads();
   return r;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so the factor of (scenario, bus) does not depend on which slot
+// or wave the scenario lands in.  key = seed, counter = (scenario lo, scenario hi, bus, 0).
+__host__ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4]) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)M0 * c0, p1 = (unsigned long long)M1 * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// truncated-normal load factor f = clip(1 + sigma * z, lo, hi), z by Box-Muller from two 53-bit uniforms in (0, 1]
+__host__ __device__ __forceinline__ double sweep_factor(unsigned long long seed, long long scen, int bus, double sigma, double lo, double hi) {
+  unsigned r[4];
+  philox4x32_10((unsigned)scen, (unsigned)((unsigned long long)scen >> 32), (unsigned)bus, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+  const double u1 = ((double)((((unsigned long long)r[0] << 32) | r[1]) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)((((unsigned long long)r[2] << 32) | r[3]) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+  const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+  const double f = 1.0 + sigma * z;
+  return f < lo ? lo : f > hi ? hi : f;
+}
+
+// the factors k_init applies in sweep mode 1, for callers / parity tests: out[s * n + bus], 1.0 on non-load buses
+__global__ void k_sweep_factors(DevModel M, long long first, int nb, unsigned long long seed, double sigma, double lo, double hi, double* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nb * M.n) return;
+  const int s = (int)(idx / M.n), bus = (int)(idx - (long long)s * M.n);
+  out[idx] = M.S0[bus].x < 0.0 ? sweep_factor(seed, first + s, bus, sigma, lo, hi) : 1.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -224,8 +263,16 @@ __global__ void __launch_bounds__(256) k_init(DevModel M, Slots A, Lists L, Batc
   const int scen = A.scen[slot];
   const size_t k = (size_t)bus * M.W + slot;
   A.V[k] = Bt.Vstart ? Bt.Vstart[bus] : M.V0[bus];
-  A.S[k] = Bt.Ssweep ? Bt.Ssweep[(size_t)scen * M.n + bus] : M.S0[bus];
-  if (A.qload_s) A.qload_s[k] = Bt.qlsweep ? Bt.qlsweep[(size_t)scen * M.n + bus] : M.qload[bus];
+  // per-scenario injections are indexed by the CALLER scenario: an island sub-scenario (id >= Btop) uses its parent's
+  const int pscen = (scen >= Bt.Btop && Bt.parent) ? Bt.parent[scen - Bt.Btop] : scen;
+  double2 Sv = Bt.Ssweep ? Bt.Ssweep[(size_t)pscen * M.n + bus] : M.S0[bus];
+  double qlv = Bt.qlsweep ? Bt.qlsweep[(size_t)pscen * M.n + bus] : M.qload[bus];
+  if (Bt.sweep_mode != 0 && Sv.x < 0.0) {          // load buses only (net consumption), P and Q scaled together
+    const double f = Bt.sweep_mode == 2 ? Bt.scale[pscen] : sweep_factor(Bt.sweep_seed, Bt.sweep_first + pscen, bus, Bt.sweep_sigma, Bt.sweep_lo, Bt.sweep_hi);
+    Sv.x *= f; Sv.y *= f; qlv *= f;
+  }
+  A.S[k] = Sv;
+  if (A.qload_s) A.qload_s[k] = qlv;
   A.type[k] = M.type0[bus];
   A.iso[k] = 0;
   A.evcnt[k] = 0;
@@ -238,6 +285,7 @@ __global__ void __launch_bounds__(256) k_init(DevModel M, Slots A, Lists L, Batc
     A.numerical[slot] = 0;
     A.reason[slot] = 1;
     A.fm[slot] = 0.0;
+    A.tiny[slot] = 0;
     int cnt = 0;
     if (Bt.out_ptr) {
       int b = Bt.out_ptr[scen], e = Bt.out_ptr[scen + 1];
@@ -801,6 +849,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
       a[2 * bi + 1] = v1;
     }
     bool sing = false;
+    int ntiny = 0;
     const unsigned full = 0xffffffffu;
     // Compact loop (fits the instruction cache): after pivot p the register column is shifted down by two
     // rows, so the pivot rows are always a[0], a[1] and every index below is a compile-time constant.
@@ -817,6 +866,8 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
       const double det = fma(p00, p11, -wq) + fma(-p01, p10, wq);
       const bool ok = isfinite(det) && det != 0.0;
       sing |= !ok;
+      const double pmx = fmax(fmax(fabs(p00), fabs(p01)), fmax(fabs(p10), fabs(p11)));
+      ntiny += (fabs(det) <= M.pivot_tol * pmx * pmx) ? 1 : 0;     // static pivoting monitor: block nearly singular relative to its own scale
       const double sc = ok ? 1.0 / det : 0.0;
       const double d00 = p11 * sc, d01 = -p01 * sc, d10 = -p10 * sc, d11 = p00 * sc;
       if (lane == 0) { Dv0[p] = make_double2(d00, d01); Dv1[p] = make_double2(d10, d11); }
@@ -847,6 +898,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
       a[2 * WR - 1] = 0.0;
     }
     if (sing && lane == 0) atomicOr(&A.singular[slot], 1);
+    if (ntiny && lane == 0) atomicAdd(&A.tiny[slot], ntiny);
     PHASE_MARK(1);   // pivot-block chain (warp 0)
     if (NT == 32) ingest_rest(tid, G);
   }
@@ -1112,6 +1164,7 @@ __global__ void __launch_bounds__(32, (NF <= 8 ? 16 : 10)) k_front_reg(DevModel 
     for (int q = vp[0]; q < vp[1]; ++q) b = cadd(b, Ca[M.reg_vsrc[q]]);
   }
   bool sing = false;
+  int ntiny = 0;
 #pragma unroll
   for (int p = 0; p < NF; ++p) {
     if (p < w) {
@@ -1121,6 +1174,8 @@ __global__ void __launch_bounds__(32, (NF <= 8 ? 16 : 10)) k_front_reg(DevModel 
       const double det = fma(p00, p11, -wq) + fma(-p01, p10, wq);      // Kahan: rounding error of the product recovered
       const bool ok = isfinite(det) && det != 0.0;
       sing |= !ok;
+      const double pmx = fmax(fmax(fabs(p00), fabs(p01)), fmax(fabs(p10), fabs(p11)));
+      ntiny += (fabs(det) <= M.pivot_tol * pmx * pmx) ? 1 : 0;
       const double sc = ok ? 1.0 / det : 0.0;
       const double d00 = p11 * sc, d01 = -p01 * sc, d10 = -p10 * sc, d11 = p00 * sc;
       if (r == p) {                                   // the pivot's owner scales its row and its rhs
@@ -1151,6 +1206,7 @@ __global__ void __launch_bounds__(32, (NF <= 8 ? 16 : 10)) k_front_reg(DevModel 
     }
   }
   if (sing && r == 0) atomicOr(&A.singular[slot], 1);
+  if (ntiny && r == 0) atomicAdd(&A.tiny[slot], ntiny);
   // ---- outputs: U' rows and y' of the pivots, update matrix + update vector of the structure rows
   if (r < w) {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4) + 2 * (size_t)(r * nf);
@@ -1633,6 +1689,8 @@ __global__ void k_fin_init(DevModel M, Slots A, Lists L) {
   A.viol[slot] = 0;
   A.maxsw[slot] = 0;
   A.rated[slot] = 0;
+  A.nvv[slot] = 0;
+  A.nov[slot] = 0;
 }
 
 // grid (ceil(n/8), ceil(nFin/32)), block (32, 8)
@@ -1654,6 +1712,13 @@ __global__ void __launch_bounds__(256) k_fin_bus(DevModel M, Slots A, Lists L, B
   if (!iso && isfinite(vm)) {
     atomicMin(&A.vmin_bits[slot], (unsigned long long)__double_as_longlong(vm));
     atomicMax(&A.vmax_bits[slot], (unsigned long long)__double_as_longlong(vm));
+    if (vm < M.vm_min || vm > M.vm_max) {            // voltage_violations (contingency.jl:160-162)
+      atomicAdd(&A.nvv[slot], 1);
+      if (Bt.viol_list) {
+        const unsigned long long q = atomicAdd(&Bt.list_counts[0], 1ull);
+        if ((long long)q < Bt.viol_cap) Bt.viol_list[q] = make_int2(scen, bus);
+      }
+    }
   }
   if (bus == M.slack) return;
   if (type == T_PV) {
@@ -1669,28 +1734,41 @@ __global__ void __launch_bounds__(256) k_fin_bus(DevModel M, Slots A, Lists L, B
 }
 
 // branch flows and loading (losses.jl:53-85, contingency.jl:165-176). grid (ceil(nbr/8), ceil(nFin/32))
-__global__ void __launch_bounds__(256) k_fin_branch(DevModel M, Slots A, Lists L) {
+__global__ void __launch_bounds__(256) k_fin_branch(DevModel M, Slots A, Lists L, Batch Bt) {
   const int nf = L.counts[3];
   const int li = blockIdx.y * 32 + threadIdx.x;
   const int br = blockIdx.x * 8 + threadIdx.y;
   if (li >= nf || br >= M.nbr) return;
   const int slot = L.fin[li];
+  const int scen = A.scen[slot];
+  double2* fl = Bt.r_flows ? Bt.r_flows + ((size_t)scen * M.nbr + br) * 2 : nullptr;
+  if (fl) { fl[0] = make_double2(0.0, 0.0); fl[1] = make_double2(0.0, 0.0); }   // out of service / not solved: zero flow
   if (!A.numerical[slot] || !M.br_status[br]) return;
-  const double rt = M.rating[br];
-  if (!(isfinite(rt) && rt > 0.0)) return;
   const int no = A.out_cnt[slot];
   for (int o = 0; o < no; ++o)
     if (A.out_br[slot * MAXOUT + o] == br) return;
   const int f = M.br_from[br], t = M.br_to[br];
   if (A.iso[(size_t)f * M.W + slot] || A.iso[(size_t)t * M.W + slot]) return;
+  const double rt = M.rating[br];
+  const bool rated = isfinite(rt) && rt > 0.0;
+  if (!rated && !fl) return;
   const double2 Vf = A.V[(size_t)f * M.W + slot], Vt = A.V[(size_t)t * M.W + slot];
   const double2 If = cadd(cmul(M.y11[br], Vf), cmul(M.y12[br], Vt));
   const double2 It = cadd(cmul(M.y22[br], Vt), cmul(M.y21[br], Vf));
   const double2 Sf = cmul(Vf, cconj(If)), St = cmul(Vt, cconj(It));
+  if (fl) { fl[0] = Sf; fl[1] = St; }
+  if (!rated) return;
   const double sf = hypot(Sf.x, Sf.y), st = hypot(St.x, St.y);
   const double loading = 100.0 * fmax(sf, st) * M.base_mva / rt;
   atomicMax(&A.load_bits[slot], abs_bits(loading));
   A.rated[slot] = 1;
+  if (loading > 100.0) {                              // overloaded_branches (contingency.jl:175)
+    atomicAdd(&A.nov[slot], 1);
+    if (Bt.over_list) {
+      const unsigned long long q = atomicAdd(&Bt.list_counts[1], 1ull);
+      if ((long long)q < Bt.over_cap) { Bt.over_list[q] = make_int2(scen, br); Bt.over_pct[q] = loading; }
+    }
+  }
 }
 
 __global__ void k_fin_write(DevModel M, Slots A, Lists L, Batch Bt) {
@@ -1711,6 +1789,9 @@ __global__ void k_fin_write(DevModel M, Slots A, Lists L, Batch Bt) {
   Bt.r_iter[scen] = A.iter[slot];
   Bt.r_nsw[scen] = A.nev[slot];
   Bt.r_fm[scen] = A.fm[slot];
+  Bt.r_nvv[scen] = conv ? A.nvv[slot] : 0;
+  Bt.r_nov[scen] = conv ? A.nov[slot] : 0;
+  Bt.r_tiny[scen] = A.tiny[slot];
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   if (conv) {
     const double vmin = bits_double(A.vmin_bits[slot]), vmax = bits_double(A.vmax_bits[slot]);
@@ -1724,14 +1805,50 @@ __global__ void k_fin_write(DevModel M, Slots A, Lists L, Batch Bt) {
   A.scen[slot] = -1;
 }
 
-// pack summary records {i32 conv,status,iter,nsw; f64 fm,vmin,vmax,load} for the NCCL gather
-__global__ void k_pack_summary(Batch Bt, unsigned char* out) {
+// Per-scenario summary records of the B CALLER scenarios (what the NCCL all-gather moves and what fetch reads back):
+// {i32 converged, status, iterations, n_switch; f64 final_mismatch, vmin, vmax, max_loading; i32 n_voltage_violations,
+// n_overloaded, island_count, n_tiny_pivots} = 64 bytes.  Scenarios decided on the host (bad branch, islanded without
+// reference) get their host verdict; island-wise composites are reduced from their sub-scenarios exactly like runpf!
+// recombines the islands (iterations summed, the first failing island fails the case with 0 iterations).
+struct SummaryRec {
+  int conv, status, iter, nsw;
+  double fm, vmin, vmax, load;
+  int nvv, nov, islands, tiny;
+};
+__global__ void k_pack_summary(Batch Bt, const int* __restrict__ host_status, const int* __restrict__ sub_first,
+                               const int* __restrict__ sub_count, const int* __restrict__ islands, SummaryRec* out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= Bt.B) return;
-  int* ip = reinterpret_cast<int*>(out + (size_t)s * 48);
-  double* dp = reinterpret_cast<double*>(out + (size_t)s * 48 + 16);
-  ip[0] = Bt.r_conv[s]; ip[1] = Bt.r_status[s]; ip[2] = Bt.r_iter[s]; ip[3] = Bt.r_nsw[s];
-  dp[0] = Bt.r_fm[s]; dp[1] = Bt.r_vmin[s]; dp[2] = Bt.r_vmax[s]; dp[3] = Bt.r_load[s];
+  if (s >= Bt.Btop) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  SummaryRec r;
+  r.islands = islands[s];
+  const int hs = host_status[s];
+  if (hs == -1) {
+    r.conv = Bt.r_conv[s]; r.status = Bt.r_status[s]; r.iter = Bt.r_iter[s]; r.nsw = Bt.r_nsw[s];
+    r.fm = Bt.r_fm[s]; r.vmin = Bt.r_vmin[s]; r.vmax = Bt.r_vmax[s]; r.load = Bt.r_load[s];
+    r.nvv = Bt.r_nvv[s]; r.nov = Bt.r_nov[s]; r.tiny = Bt.r_tiny[s];
+  } else if (hs == -2) {
+    r.conv = 1; r.status = 0; r.iter = 0; r.nsw = 0; r.fm = 0.0; r.vmin = nan; r.vmax = nan; r.load = nan;
+    r.nvv = 0; r.nov = 0; r.tiny = 0;
+    bool any_ld = false;
+    for (int q = 0; q < sub_count[s]; ++q) {
+      const int u = sub_first[s] + q;
+      r.tiny += Bt.r_tiny[u];
+      if (!Bt.r_conv[u]) { r.conv = 0; r.status = Bt.r_status[u]; r.iter = 0; break; }
+      r.iter += Bt.r_iter[u]; r.nsw += Bt.r_nsw[u];
+      r.fm = fmax(r.fm, Bt.r_fm[u]);
+      r.vmin = isnan(r.vmin) ? Bt.r_vmin[u] : fmin(r.vmin, Bt.r_vmin[u]);
+      r.vmax = isnan(r.vmax) ? Bt.r_vmax[u] : fmax(r.vmax, Bt.r_vmax[u]);
+      const double ld = Bt.r_load[u];
+      if (!isnan(ld)) { r.load = any_ld ? fmax(r.load, ld) : ld; any_ld = true; }
+      r.nvv += Bt.r_nvv[u]; r.nov += Bt.r_nov[u];
+    }
+    if (!r.conv) { r.fm = nan; r.vmin = nan; r.vmax = nan; r.load = nan; r.nsw = 0; r.nvv = 0; r.nov = 0; }
+  } else {
+    r.conv = 0; r.status = hs; r.iter = 0; r.nsw = 0; r.fm = nan; r.vmin = nan; r.vmax = nan; r.load = nan;
+    r.nvv = 0; r.nov = 0; r.tiny = 0;
+  }
+  out[s] = r;
 }
 
 }  // namespace sblx

@@ -99,28 +99,35 @@ class Engine:
         self.n = arrays.n
         self.base = int(index_base)
         self.opt = L.default_options(index_base=self.base, base_mva=arrays.baseMVA, **options)
+        k = self._pack_model(arrays, self.base)
+        self._keep = k
+        h = C.c_void_p()
+        rc = self.lib.sblx_create(C.byref(h), self.n, *self._model_args(k, arrays, self.base), C.byref(self.opt))
+        L.check(rc, None)
+        self.h = h
+
+    @staticmethod
+    def _pack_model(arrays, base):
         Y = arrays.Y.tocsc()
         Y.sort_indices()
-        self._keep = dict(
-            colptr=np.ascontiguousarray(Y.indptr + self.base, np.int64), rowval=np.ascontiguousarray(Y.indices + self.base, np.int64),
+        return dict(
+            colptr=np.ascontiguousarray(Y.indptr + base, np.int64), rowval=np.ascontiguousarray(Y.indices + base, np.int64),
             nz=L.c128_to_f64(Y.data), bt=np.ascontiguousarray(arrays.bus_type, np.uint8),
             vset=np.ascontiguousarray(arrays.vset, float), s=L.c128_to_f64(arrays.s_spec), v0=L.c128_to_f64(arrays.v0),
             qmin=np.ascontiguousarray(arrays.qmin, float), qmax=np.ascontiguousarray(arrays.qmax, float),
-            ql=np.ascontiguousarray(arrays.qload, float), bf=np.ascontiguousarray(np.asarray(arrays.br_from) + self.base, np.int32),
-            bt2=np.ascontiguousarray(np.asarray(arrays.br_to) + self.base, np.int32), y11=L.c128_to_f64(arrays.y11), y12=L.c128_to_f64(arrays.y12),
+            ql=np.ascontiguousarray(arrays.qload, float), bf=np.ascontiguousarray(np.asarray(arrays.br_from) + base, np.int32),
+            bt2=np.ascontiguousarray(np.asarray(arrays.br_to) + base, np.int32), y11=L.c128_to_f64(arrays.y11), y12=L.c128_to_f64(arrays.y12),
             y21=L.c128_to_f64(arrays.y21), y22=L.c128_to_f64(arrays.y22),
             rt=np.ascontiguousarray(arrays.br_rating, float), st=np.ascontiguousarray(arrays.br_status, np.uint8))
-        k = self._keep
-        h = C.c_void_p()
-        rc = self.lib.sblx_create(C.byref(h), self.n, L.ptr(k["colptr"], L.c_i64p), L.ptr(k["rowval"], L.c_i64p),
-                                  L.ptr(k["nz"], L.c_f64p), arrays.slack + self.base, L.ptr(k["bt"], L.c_u8p), L.ptr(k["vset"], L.c_f64p),
-                                  L.ptr(k["s"], L.c_f64p), L.ptr(k["v0"], L.c_f64p), L.ptr(k["qmin"], L.c_f64p),
-                                  L.ptr(k["qmax"], L.c_f64p), L.ptr(k["ql"], L.c_f64p), len(arrays.br_from),
-                                  L.ptr(k["bf"], L.c_i32p), L.ptr(k["bt2"], L.c_i32p), L.ptr(k["y11"], L.c_f64p),
-                                  L.ptr(k["y12"], L.c_f64p), L.ptr(k["y21"], L.c_f64p), L.ptr(k["y22"], L.c_f64p),
-                                  L.ptr(k["rt"], L.c_f64p), L.ptr(k["st"], L.c_u8p), C.byref(self.opt))
-        L.check(rc, None)
-        self.h = h
+
+    @staticmethod
+    def _model_args(k, arrays, base):
+        """argument tail shared by sblx_create and sblx_create_multi (from colptr to br_status)"""
+        return (L.ptr(k["colptr"], L.c_i64p), L.ptr(k["rowval"], L.c_i64p), L.ptr(k["nz"], L.c_f64p), arrays.slack + base,
+                L.ptr(k["bt"], L.c_u8p), L.ptr(k["vset"], L.c_f64p), L.ptr(k["s"], L.c_f64p), L.ptr(k["v0"], L.c_f64p),
+                L.ptr(k["qmin"], L.c_f64p), L.ptr(k["qmax"], L.c_f64p), L.ptr(k["ql"], L.c_f64p), len(arrays.br_from),
+                L.ptr(k["bf"], L.c_i32p), L.ptr(k["bt2"], L.c_i32p), L.ptr(k["y11"], L.c_f64p), L.ptr(k["y12"], L.c_f64p),
+                L.ptr(k["y21"], L.c_f64p), L.ptr(k["y22"], L.c_f64p), L.ptr(k["rt"], L.c_f64p), L.ptr(k["st"], L.c_u8p))
 
     def close(self):
         if getattr(self, "h", None):
@@ -154,14 +161,27 @@ class Engine:
 
     # -- solves -------------------------------------------------------------
     @staticmethod
-    def _alloc(B, n, want_v, want_types):
+    def _alloc(B, n, want_v, want_types, want_lists=False, want_flows=False, nbranch=0, list_capacity=0):
         r = dict(converged=np.zeros(B, np.uint8), status=np.zeros(B, np.int32), iterations=np.zeros(B, np.int32),
                  n_switch_events=np.zeros(B, np.int32), island_count=np.zeros(B, np.int32),
-                 final_mismatch=np.zeros(B), vmin_pu=np.zeros(B), vmax_pu=np.zeros(B), max_loading_pct=np.zeros(B))
+                 final_mismatch=np.zeros(B), vmin_pu=np.zeros(B), vmax_pu=np.zeros(B), max_loading_pct=np.zeros(B),
+                 n_voltage_violations=np.zeros(B, np.int32), n_overloaded=np.zeros(B, np.int32),
+                 n_tiny_pivots=np.zeros(B, np.int32))
         if want_v:
             r["V"] = np.zeros((B, n), np.complex128)
         if want_types:
             r["bus_type_final"] = np.zeros((B, n), np.uint8)
+        if want_lists:
+            cap = int(list_capacity) if list_capacity else 16 * B + 65536
+            r["_viol_scenario"] = np.zeros(cap, np.int32)
+            r["_viol_bus"] = np.zeros(cap, np.int32)
+            r["_viol_count"] = np.zeros(1, np.int64)
+            r["_over_scenario"] = np.zeros(cap, np.int32)
+            r["_over_branch"] = np.zeros(cap, np.int32)
+            r["_over_pct"] = np.zeros(cap)
+            r["_over_count"] = np.zeros(1, np.int64)
+        if want_flows:
+            r["flows"] = np.zeros((B, nbranch, 2), np.complex128)
         return r
 
     @staticmethod
@@ -178,7 +198,34 @@ class Engine:
         s.max_loading_pct = L.ptr(r["max_loading_pct"], L.c_f64p)
         s.V = L.ptr(r["V"].view(np.float64), L.c_f64p) if "V" in r else None
         s.bus_type_final = L.ptr(r["bus_type_final"], L.c_u8p) if "bus_type_final" in r else None
+        s.n_voltage_violations = L.ptr(r["n_voltage_violations"], L.c_i32p)
+        s.n_overloaded = L.ptr(r["n_overloaded"], L.c_i32p)
+        s.n_tiny_pivots = L.ptr(r["n_tiny_pivots"], L.c_i32p)
+        if "_viol_scenario" in r:
+            s.viol_capacity = len(r["_viol_scenario"])
+            s.viol_scenario = L.ptr(r["_viol_scenario"], L.c_i32p)
+            s.viol_bus = L.ptr(r["_viol_bus"], L.c_i32p)
+            s.viol_count = L.ptr(r["_viol_count"], L.c_i64p)
+            s.over_capacity = len(r["_over_scenario"])
+            s.over_scenario = L.ptr(r["_over_scenario"], L.c_i32p)
+            s.over_branch = L.ptr(r["_over_branch"], L.c_i32p)
+            s.over_loading_pct = L.ptr(r["_over_pct"], L.c_f64p)
+            s.over_count = L.ptr(r["_over_count"], L.c_i64p)
+        s.flows = L.ptr(r["flows"].view(np.float64), L.c_f64p) if "flows" in r else None
         return s
+
+    def _finish_lists(self, r):
+        """trim the compacted (scenario, element) lists to their counts and shift ids back to 0-based"""
+        if "_viol_scenario" not in r:
+            return r
+        nv, no = int(r["_viol_count"][0]), int(r["_over_count"][0])
+        r["lists_complete"] = nv <= len(r["_viol_scenario"]) and no <= len(r["_over_scenario"])
+        nv, no = min(nv, len(r["_viol_scenario"])), min(no, len(r["_over_scenario"]))
+        r["violations"] = np.stack([r.pop("_viol_scenario")[:nv], r.pop("_viol_bus")[:nv] - self.base], axis=1)
+        r["overloads"] = np.stack([r.pop("_over_scenario")[:no], r.pop("_over_branch")[:no] - self.base], axis=1)
+        r["overload_pct"] = r.pop("_over_pct")[:no]
+        r["violation_total"], r["overload_total"] = int(r.pop("_viol_count")[0]), int(r.pop("_over_count")[0])
+        return r
 
     @staticmethod
     def pack_outages(cases):
@@ -189,16 +236,35 @@ class Engine:
         br = np.array([b for c in cases for b in c], np.int32) if ptr[-1] > 0 else np.zeros(1, np.int32)
         return ptr, br
 
-    def solve_outages(self, cases, want_v=True, want_types=True) -> dict:
-        B = len(cases)
+    def solve_outages(self, cases, want_v=True, want_types=True, want_lists=False, want_flows=False, list_capacity=0,
+                      sharded=False) -> dict:
+        """`want_lists`: compacted (scenario, bus) voltage-violation and (scenario, branch) overload lists computed on the
+        device (r["violations"], r["overloads"], r["overload_pct"]); `want_flows`: per-branch complex flows [B, nbranch, 2];
+        `sharded`: collective call over the communicator set with `comm_init` (every rank passes the same batch)."""
         optr, obr = self.pack_outages(cases) if not isinstance(cases, tuple) else cases
         B = len(optr) - 1
         if self.base:
             obr = np.ascontiguousarray(obr + self.base, np.int32)
-        r = self._alloc(B, self.n, want_v, want_types)
+        r = self._alloc(B, self.n, want_v, want_types, want_lists, want_flows, len(self.a.br_from), list_capacity)
         s = self._results_struct(r)
-        L.check(self.lib.sblx_solve_outages(self.h, B, L.ptr(optr, L.c_i32p), L.ptr(obr, L.c_i32p), C.byref(s)), self.h)
-        return r
+        fn = self.lib.sblx_solve_outages_sharded if sharded else self.lib.sblx_solve_outages
+        L.check(fn(self.h, B, L.ptr(optr, L.c_i32p), L.ptr(obr, L.c_i32p), C.byref(s)), self.h)
+        return self._finish_lists(r)
+
+    # -- multi-GPU (one process per GPU): NCCL communicator inside the library ----------------
+    def comm_unique_id(self) -> bytes:
+        buf = np.zeros(128, np.uint8)
+        L.check(self.lib.sblx_comm_unique_id(L.ptr(buf, L.c_u8p)), None)
+        return buf.tobytes()
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        buf = np.frombuffer(uid, np.uint8).copy()
+        L.check(self.lib.sblx_comm_init_rank(self.h, nranks, rank, L.ptr(buf, L.c_u8p)), self.h)
+
+    def shard_bounds(self, B: int, nranks: int):
+        b = np.zeros(nranks + 1, np.int64)
+        L.check(self.lib.sblx_shard_bounds(self.h, B, None, None, nranks, L.ptr(b, L.c_i64p)), self.h)
+        return b
 
     def stage_outages(self, optr, obr, want_v=False, want_types=False):
         if self.base:
@@ -230,6 +296,30 @@ class Engine:
         s = self._results_struct(r)
         ql = None if qload is None else np.ascontiguousarray(qload, float)
         L.check(self.lib.sblx_solve_injections(self.h, B, L.ptr(S.view(np.float64), L.c_f64p), L.ptr(ql, L.c_f64p), C.byref(s)), self.h)
+        return r
+
+    def sweep(self, n_scen, first=0, seed=20260724, sigma=0.1, lo=0.5, hi=1.5, want_v=False, want_types=False, want_lists=False):
+        """Device-side injection sweep (BASELINE config 4): per scenario an independent truncated-normal factor
+        f = clip(1 + sigma z, lo, hi) on P and Q of every load bus, drawn ON THE GPU from Philox4x32-10 keyed on
+        (seed, first + scenario, bus) - the reference's Monte-Carlo recipe (examples/powerflow/mc_probabilistic_powerflow.jl:28-41);
+        only the parameters cross PCIe."""
+        r = self._alloc(n_scen, self.n, want_v, want_types, want_lists)
+        s = self._results_struct(r)
+        L.check(self.lib.sblx_solve_injection_sweep(self.h, n_scen, first, seed, sigma, lo, hi, C.byref(s)), self.h)
+        return self._finish_lists(r)
+
+    def sweep_factors(self, n_scen, first=0, seed=20260724, sigma=0.1, lo=0.5, hi=1.5):
+        """the factors `sweep` applies, [n_scen, n] (1.0 on non-load buses), evaluated by the same device code"""
+        out = np.zeros((n_scen, self.n))
+        L.check(self.lib.sblx_sweep_factors(self.h, n_scen, first, seed, sigma, lo, hi, L.ptr(out, L.c_f64p)), self.h)
+        return out
+
+    def scale_sweep(self, scale, want_v=False, want_types=False):
+        """one load-scaling factor per scenario (uniform scaling of all load buses)"""
+        sc = np.ascontiguousarray(scale, float)
+        r = self._alloc(len(sc), self.n, want_v, want_types)
+        s = self._results_struct(r)
+        L.check(self.lib.sblx_solve_injection_scale(self.h, len(sc), L.ptr(sc, L.c_f64p), C.byref(s)), self.h)
         return r
 
     def injection_sweep(self, s_spec0, qload0, n_scen, seed=20260724, sigma=0.1, lo=0.5, hi=1.5, chunk=4096):
@@ -439,12 +529,32 @@ def _resolve_branch(grid, element: str):
     return None
 
 
+def _solve_with_lists(eng, lists, return_raw):
+    """one batched call; voltage-violation / overload lists come compacted from the device, so the bus voltages only
+    cross PCIe when the caller asks for the raw arrays"""
+    raw = eng.solve_outages(lists, want_v=return_raw, want_types=return_raw, want_lists=True)
+    if not raw["lists_complete"]:
+        raw = eng.solve_outages(lists, want_v=return_raw, want_types=return_raw, want_lists=True,
+                                list_capacity=max(raw["violation_total"], raw["overload_total"]) + 16)
+    return raw
+
+
+def _group(pairs, B):
+    """(scenario, element) rows sorted by scenario -> list of element arrays per scenario"""
+    out = [[] for _ in range(B)]
+    for sc, el in pairs:
+        out[int(sc)].append(int(el))
+    return out
+
+
 def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30, tol=1e-8, backend=None,
-                            return_raw=False, retry_flat_start=False, **kwargs):
+                            return_raw=False, retry_flat_start=False, n_devices=1, **kwargs):
     """runContingencies! (src/contingency.jl:257-319) with the batched B200 backend: the
     base case is solved first (warm-start template; on failure the cases start flat), then
-    ALL cases go to the GPU in one call.  Results come back in input order.  `retry_flat_start`: the cases that did
-    not converge get one second batch from a flat start, iterations summed (contingency.jl:195-207)."""
+    ALL cases go to the GPU(s) in one call.  Results come back in input order.  `retry_flat_start`: the cases that did
+    not converge get one second batch from a flat start, iterations summed (contingency.jl:195-207).
+    `n_devices` > 1: the cases are sharded over that many GPUs of this process inside the library (contiguous chunks
+    like contingency.jl:304, one ncclAllGather of the per-case records)."""
     if not (vm_min_pu < vm_max_pu):
         raise ValueError("runContingencies!: vm_min_pu must be below vm_max_pu.")
     if len(cases) == 0:
@@ -453,8 +563,9 @@ def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30
     opts.update(kwargs)
     opts.update(max_iter=maxIte, tol=tol, vm_min_pu=vm_min_pu, vm_max_pu=vm_max_pu,
                 cooldown_iters=grid.cooldown_iters, q_hyst_pu=grid.q_hyst_pu)
+    mk = (lambda arr: MultiEngine(arr, n_devices, **opts)) if n_devices > 1 else (lambda arr: Engine(arr, **opts))
     a = M.build_arrays(grid)
-    eng = Engine(a, **opts)
+    eng = mk(a)
     try:
         Vb, conv, _, _, _ = eng.solve_one(None)
         if conv:
@@ -464,25 +575,28 @@ def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30
         else:
             a2 = M.build_arrays(grid, flatstart=True)           # contingency.jl:283-287
             eng.close()
-            eng = Engine(a2, **opts)                              # Vset may differ for a flat start
+            eng = mk(a2)                                          # Vset may differ for a flat start
         eng.set_v0(a2.v0)
         idx = [_resolve_branch(grid, c.element) for c in cases]
         lists = [[k] if k is not None else [-1] for k in idx]
-        raw = eng.solve_outages(lists, want_v=True, want_types=return_raw)
+        raw = _solve_with_lists(eng, lists, return_raw)
+        viol, over = _group(raw["violations"], len(cases)), _group(raw["overloads"], len(cases))
         if retry_flat_start:
             again = [i for i in range(len(cases)) if idx[i] is not None and not raw["converged"][i] and 1 <= int(raw["status"][i]) <= 6]
             if again:
                 eng.close()
                 vmt, vat = (np.abs(Vb), np.degrees(np.angle(Vb))) if conv else (None, None)
                 a3 = M.build_arrays(grid, vm=vmt, va_deg=vat, flatstart=True)     # cnet.flatstart = true on the template copy
-                eng = Engine(a3, **opts)
-                raw2 = eng.solve_outages([lists[i] for i in again], want_v=True, want_types=return_raw)
+                eng = mk(a3)
+                raw2 = _solve_with_lists(eng, [lists[i] for i in again], return_raw)
+                v2, o2 = _group(raw2["violations"], len(again)), _group(raw2["overloads"], len(again))
                 for j, i in enumerate(again):
                     it1 = int(raw["iterations"][i])
                     for key, arr in raw.items():
-                        if arr is not None and raw2.get(key) is not None:
+                        if isinstance(arr, np.ndarray) and len(arr) == len(cases) and isinstance(raw2.get(key), np.ndarray):
                             arr[i] = raw2[key][j]
                     raw["iterations"][i] += it1
+                    viol[i], over[i] = v2[j], o2[j]
     finally:
         eng.close()
     out = []
@@ -496,30 +610,75 @@ def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30
             out.append(ContingencyResult(c.name, False, int(raw["iterations"][i]), math.nan, math.nan, math.nan, [], [],
                                          int(raw["island_count"][i]), STATUS_TEXT.get(st, f"status {st}")))
             continue
-        V = raw["V"][i]
-        vmag = np.abs(V)
-        deg = np.bincount(np.concatenate([grid.br_from, grid.br_to]),
-                          weights=np.concatenate([grid.br_status == 1, grid.br_status == 1]).astype(float), minlength=grid.n)
-        k = idx[i]
-        deg[grid.br_from[k]] -= 1
-        deg[grid.br_to[k]] -= 1
-        live = deg > 0
-        viol = [grid.bus_name[b] for b in np.flatnonzero(live & ((vmag < vm_min_pu) | (vmag > vm_max_pu)))]
-        over = []
-        if np.isfinite(raw["max_loading_pct"][i]) and raw["max_loading_pct"][i] > 100.0:
-            y11, y12, y21, y22 = a.y11, a.y12, a.y21, a.y22
-            f, t = grid.br_from, grid.br_to
-            sf = np.abs(V[f] * np.conj(y11 * V[f] + y12 * V[t]))
-            stt = np.abs(V[t] * np.conj(y22 * V[t] + y21 * V[f]))
-            with np.errstate(invalid="ignore", divide="ignore"):
-                loading = 100.0 * np.maximum(sf, stt) * grid.baseMVA / grid.br_rating
-            ok = (grid.br_status == 1) & np.isfinite(grid.br_rating) & (grid.br_rating > 0)
-            ok[k] = False
-            over = [grid.br_name[b] for b in np.flatnonzero(ok & (loading > 100.0))]
         out.append(ContingencyResult(c.name, True, int(raw["iterations"][i]), float(raw["vmax_pu"][i]),
-                                     float(raw["vmin_pu"][i]), float(raw["max_loading_pct"][i]), over, viol,
+                                     float(raw["vmin_pu"][i]), float(raw["max_loading_pct"][i]),
+                                     [grid.br_name[b] for b in over[i]], [grid.bus_name[b] for b in viol[i]],
                                      int(raw["island_count"][i]), None))
     return (out, raw) if return_raw else out
+
+
+class MultiEngine:
+    """One process, several GPUs (sblx_create_multi): the same model on `n_devices` B200s, batches sharded inside the
+    library with one ncclAllGather of the per-scenario records.  Same solve interface as `Engine`."""
+
+    def __init__(self, arrays: M.ModelArrays, n_devices: int, devices=None, index_base: int = 0, **options):
+        self.lib = L.load()
+        self.a, self.n, self.base, self.nd = arrays, arrays.n, int(index_base), int(n_devices)
+        self.opt = L.default_options(index_base=self.base, base_mva=arrays.baseMVA, **options)
+        k = Engine._pack_model(arrays, self.base)
+        self._keep = k
+        dv = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        rc = self.lib.sblx_create_multi(C.byref(h), self.nd, L.ptr(dv, L.c_i32p), self.n, *Engine._model_args(k, arrays, self.base), C.byref(self.opt))
+        L.check(rc, None)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sblx_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.sblx_multi_last_error(self.h)
+            raise L.SblxError(f"sblx error {rc}: {msg.decode() if msg else ''}")
+
+    def set_v0(self, v0):
+        self._check(self.lib.sblx_multi_set_v0(self.h, L.ptr(L.c128_to_f64(v0), L.c_f64p)))
+
+    def set_locked_pv(self, buses):
+        b = np.ascontiguousarray(np.asarray(buses, np.int64) + self.base, np.int32)
+        self._check(self.lib.sblx_multi_set_locked_pv(self.h, len(b), L.ptr(b, L.c_i32p)))
+
+    def stats(self, dev_index=0) -> dict:
+        s = L.Stats()
+        self._check(self.lib.sblx_multi_get_stats(self.h, dev_index, C.byref(s)))
+        return L.as_dict(s)
+
+    def solve_one(self, v_start=None):
+        h0 = self.lib.sblx_multi_handle(self.h, 0)
+        vout = np.zeros(self.n, np.complex128)
+        c, it, res, st = C.c_uint8(), C.c_int32(), C.c_double(), C.c_int32()
+        vs = None if v_start is None else L.c128_to_f64(v_start)
+        L.check(self.lib.sblx_solve_one(h0, L.ptr(vs, L.c_f64p), L.ptr(vout.view(np.float64), L.c_f64p), C.byref(c),
+                                        C.byref(it), C.byref(res), C.byref(st)), h0)
+        return vout, bool(c.value), int(it.value), float(res.value), int(st.value)
+
+    def solve_outages(self, cases, want_v=True, want_types=True, want_lists=False, want_flows=False, list_capacity=0) -> dict:
+        optr, obr = Engine.pack_outages(cases) if not isinstance(cases, tuple) else cases
+        B = len(optr) - 1
+        if self.base:
+            obr = np.ascontiguousarray(obr + self.base, np.int32)
+        r = Engine._alloc(B, self.n, want_v, want_types, want_lists, want_flows, len(self.a.br_from), list_capacity)
+        s = Engine._results_struct(r)
+        self._check(self.lib.sblx_multi_solve_outages(self.h, B, L.ptr(optr, L.c_i32p), L.ptr(obr, L.c_i32p), C.byref(s)))
+        return Engine._finish_lists(self, r)
 
 
 # ---------------------------------------------------------------------------

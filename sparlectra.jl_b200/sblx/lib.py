@@ -25,7 +25,7 @@ class Options(C.Structure):
         ("factor_mode", C.c_int32), ("reserved1", C.c_int32),
         ("tol", C.c_double), ("damp", C.c_double), ("q_hyst_pu", C.c_double), ("vm_min_pu", C.c_double),
         ("vm_max_pu", C.c_double), ("base_mva", C.c_double), ("mem_fraction", C.c_double),
-        ("relax_zero_frac", C.c_double), ("panel_smem_kb", C.c_double),
+        ("relax_zero_frac", C.c_double), ("panel_smem_kb", C.c_double), ("pivot_tol_rel", C.c_double),
     ]
 
 
@@ -34,6 +34,10 @@ class Results(C.Structure):
         ("converged", c_u8p), ("status", c_i32p), ("iterations", c_i32p), ("n_switch_events", c_i32p),
         ("island_count", c_i32p), ("final_mismatch", c_f64p), ("vmin_pu", c_f64p), ("vmax_pu", c_f64p),
         ("max_loading_pct", c_f64p), ("V", c_f64p), ("bus_type_final", c_u8p),
+        ("n_voltage_violations", c_i32p), ("n_overloaded", c_i32p), ("n_tiny_pivots", c_i32p),
+        ("viol_capacity", C.c_int64), ("viol_scenario", c_i32p), ("viol_bus", c_i32p), ("viol_count", c_i64p),
+        ("over_capacity", C.c_int64), ("over_scenario", c_i32p), ("over_branch", c_i32p), ("over_loading_pct", c_f64p),
+        ("over_count", c_i64p), ("flows", c_f64p),
     ]
 
 
@@ -53,6 +57,8 @@ class Stats(C.Structure):
         ("host_prep_ms", C.c_double), ("launches", C.c_int64), ("factor_launches", C.c_int64), ("ticks", C.c_int64),
         ("scenario_iterations", C.c_int64), ("mismatch_evaluations", C.c_int64), ("scenarios_solved", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("tiny_pivots", C.c_int64), ("n_ranks", C.c_int64), ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
+        ("allgather_ms", C.c_double),
     ]
 
 
@@ -61,7 +67,10 @@ EXPORTS = [
     "sblx_set_v0", "sblx_get_info", "sblx_get_stats", "sblx_solve_outages", "sblx_solve_injections", "sblx_solve_one",
     "sblx_stage_outages", "sblx_run_staged", "sblx_fetch_results", "sblx_device_summary", "sblx_debug_pattern",
     "sblx_debug_newton_step", "sblx_debug_host_selftest", "sblx_analyze_only", "sblx_debug_phase_cycles",
-    "sblx_debug_topology",
+    "sblx_debug_topology", "sblx_solve_injection_sweep", "sblx_solve_injection_scale", "sblx_sweep_factors",
+    "sblx_comm_unique_id", "sblx_comm_init_rank", "sblx_comm_destroy", "sblx_solve_outages_sharded", "sblx_shard_bounds",
+    "sblx_create_multi", "sblx_destroy_multi", "sblx_multi_last_error", "sblx_multi_set_v0", "sblx_multi_set_locked_pv",
+    "sblx_multi_solve_outages", "sblx_multi_get_stats", "sblx_multi_handle",
 ]
 
 _lib = None
@@ -105,6 +114,25 @@ def load():
     lib.sblx_debug_phase_cycles.argtypes = [c_f64p]
     lib.sblx_debug_topology.argtypes = [C.c_int64, C.c_int64, c_u8p, C.c_int64, c_i32p, c_i32p, c_u8p, C.c_int32, C.c_int64, c_i32p,
                                         c_i32p, c_i32p, c_i32p, c_i32p]
+    lib.sblx_solve_injection_sweep.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.POINTER(Results)]
+    lib.sblx_solve_injection_scale.argtypes = [vp, C.c_int64, c_f64p, C.POINTER(Results)]
+    lib.sblx_sweep_factors.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, c_f64p]
+    lib.sblx_comm_unique_id.argtypes = [c_u8p]
+    lib.sblx_comm_init_rank.argtypes = [vp, C.c_int32, C.c_int32, c_u8p]
+    lib.sblx_comm_destroy.argtypes = [vp]
+    lib.sblx_solve_outages_sharded.argtypes = [vp, C.c_int64, c_i32p, c_i32p, C.POINTER(Results)]
+    lib.sblx_shard_bounds.argtypes = [vp, C.c_int64, c_i32p, c_i32p, C.c_int32, c_i64p]
+    lib.sblx_create_multi.argtypes = [C.POINTER(vp), C.c_int32, c_i32p] + lib.sblx_create.argtypes[1:]
+    lib.sblx_destroy_multi.argtypes = [vp]
+    lib.sblx_destroy_multi.restype = None
+    lib.sblx_multi_last_error.argtypes = [vp]
+    lib.sblx_multi_last_error.restype = C.c_char_p
+    lib.sblx_multi_set_v0.argtypes = [vp, c_f64p]
+    lib.sblx_multi_set_locked_pv.argtypes = [vp, C.c_int64, c_i32p]
+    lib.sblx_multi_solve_outages.argtypes = [vp, C.c_int64, c_i32p, c_i32p, C.POINTER(Results)]
+    lib.sblx_multi_get_stats.argtypes = [vp, C.c_int32, C.POINTER(Stats)]
+    lib.sblx_multi_handle.argtypes = [vp, C.c_int32]
+    lib.sblx_multi_handle.restype = vp
     for name in EXPORTS:
         if getattr(lib, name).restype is C.c_int and name not in ("sblx_version",):
             getattr(lib, name).restype = C.c_int

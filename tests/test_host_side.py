@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "sblx.h")).read()
     declared = set(re.findall(r"\b(sblx_[a-z0-9_]+)\s*\(", hdr))
     lib = L.load()
-    assert lib.sblx_version() == 100
+    assert lib.sblx_version() == 200
     assert len(declared) >= 20
     for name in declared:
         assert hasattr(lib, name), name
