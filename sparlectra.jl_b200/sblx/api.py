@@ -529,6 +529,10 @@ def _resolve_branch(grid, element: str):
     return None
 
 
+PER_SCENARIO_KEYS = ("converged", "status", "iterations", "n_switch_events", "island_count", "final_mismatch", "vmin_pu", "vmax_pu",
+                     "max_loading_pct", "n_voltage_violations", "n_overloaded", "n_tiny_pivots", "V", "bus_type_final", "flows")
+
+
 def _solve_with_lists(eng, lists, return_raw):
     """one batched call; voltage-violation / overload lists come compacted from the device, so the bus voltages only
     cross PCIe when the caller asks for the raw arrays"""
@@ -592,9 +596,9 @@ def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30
                 v2, o2 = _group(raw2["violations"], len(again)), _group(raw2["overloads"], len(again))
                 for j, i in enumerate(again):
                     it1 = int(raw["iterations"][i])
-                    for key, arr in raw.items():
-                        if isinstance(arr, np.ndarray) and len(arr) == len(cases) and isinstance(raw2.get(key), np.ndarray):
-                            arr[i] = raw2[key][j]
+                    for key in PER_SCENARIO_KEYS:
+                        if key in raw and key in raw2:
+                            raw[key][i] = raw2[key][j]
                     raw["iterations"][i] += it1
                     viol[i], over[i] = v2[j], o2[j]
     finally:

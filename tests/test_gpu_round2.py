@@ -53,6 +53,12 @@ def _warm_engine(g, **opts):
     return api.Engine(a, cooldown_iters=g.cooldown_iters, q_hyst_pu=g.q_hyst_pu, **opts), a, vm, va
 
 
+def _ladder_split(g):
+    ka = [k for k in range(g.nbranch) if (g.br_from[k], g.br_to[k]) == (14, 15)][0]
+    kb = [k for k in range(g.nbranch) if (g.br_from[k], g.br_to[k]) == (73, 74)][0]
+    return [ka, kb]
+
+
 def test_device_lists_and_flows_match_oracle_metrics():
     """overloaded_branches / voltage_violations (contingency.jl:149-178) and the branch flows (losses.jl:53-85) come
     from the device; checked per scenario against the oracle's _contingency_metrics / branch_flows."""
@@ -108,14 +114,9 @@ def test_device_summary_equals_fetched_results_with_islands_and_bad_branches():
     import ctypes
     g = G.warmup_case118()
     eng, a, vm, va = _warm_engine(g)
-    split = None
-    for k in range(g.nbranch):       # a branch whose loss splits the ladder into two referenced islands
-        isl, st, _ = api.topology_only(a, [[k]])
-        if st[0] == -2:
-            split = k
-            break
-    assert split is not None
-    cases = [[0], [split], [10 ** 6], [2, 5], [], [split, 3]]
+    split = _ladder_split(g)          # both rails out: two islands with a reference each
+    assert api.topology_only(a, [split])[1][0] == -2
+    cases = [[0], split, [10 ** 6], [2, 5], [], split + [3]]
     raw = eng.solve_outages(cases)
     ptr, nbytes = eng.device_summary()
     assert nbytes == len(cases) * shard.RECORD_BYTES
@@ -225,10 +226,8 @@ def test_scale_sweep_matches_oracle():
 def test_injection_sweep_on_a_two_island_base_grid():
     """island sub-scenarios (device ids >= B) must read their PARENT scenario's injections."""
     g = G.warmup_case118()
-    a0 = M.build_arrays(g)
-    split = next(k for k in range(g.nbranch) if api.topology_only(a0, [[k]])[1][0] == -2)
     g.br_status = np.array(g.br_status).copy()
-    g.br_status[split] = 0                       # the intact grid already consists of two referenced islands
+    g.br_status[_ladder_split(g)] = 0            # the intact grid already consists of two referenced islands
     vm, va, flat, base = O.solve_base(g)
     assert base.converged and base.island_count == 2
     a = M.build_arrays(g, vm=vm, va_deg=va)

@@ -3,6 +3,6 @@
 cd "$(dirname "$0")/.."
 for spec in "$@"; do
   label=${spec%%|*}; args=${spec#*|}
-  out=$(python bench.py --steps 2 --warmup 1 --no-cpu-baseline $args 2>&1 | python tools/brief.py)
+  out=$(python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-api-e2e $args 2>&1 | python tools/brief.py)
   echo "$label :: $out"
 done
