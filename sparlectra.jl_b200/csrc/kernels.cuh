@@ -610,6 +610,13 @@ __global__ void __launch_bounds__(256) k_jacobian(DevModel M, Slots A, Lists L) 
   }
 }
 
+// Phase ablation build (-DSBLX_ABLATE, tools only): bits of SBLX_PF_MODE >= 8 switch phases of k_front OFF so that their
+// real cost (with all the overlap between co-resident CTAs) shows up as a time difference.  Results are garbage.
+#ifdef SBLX_ABLATE
+#define ABL(bit) ((M.pf_mode & (bit)) != 0)
+#else
+#define ABL(bit) false
+#endif
 #ifdef SBLX_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[5][10];   // [class][phase]; [9] = CTA count
 #define PHASE_MARK(ph)                                                                             \
@@ -665,7 +672,16 @@ template <int NT, int G = NT, bool WIDE = false>
 #ifndef SBLX_OCC128
 #define SBLX_OCC128 3
 #endif
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : NT == 128 ? SBLX_OCC128 : NT == 64 ? (WIDE ? 6 : 10) : NT == 32 ? (G < 32 ? 8 : 16) : 1))
+#ifndef SBLX_OCC32G
+#define SBLX_OCC32G 8
+#endif
+#ifndef SBLX_OCC64
+#define SBLX_OCC64 10
+#endif
+#ifndef SBLX_OCC256
+#define SBLX_OCC256 2
+#endif
+__global__ void __launch_bounds__(NT, (NT == 256 ? SBLX_OCC256 : NT == 128 ? SBLX_OCC128 : NT == 64 ? (WIDE ? 6 : SBLX_OCC64) : NT == 32 ? (G < 32 ? SBLX_OCC32G : 16) : 1))
 k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels, int group_stride, int pf_delta) {
   static_assert(G == NT || NT == 32, "lane groups need a one-warp CTA");
   extern __shared__ double2 sm2_all[];
@@ -812,7 +828,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
     }
   }
   // the rest of the panel: the pivot rows right of the pivot block, then all structure-row blocks
-  auto ingest_rest = [&](int t0, int tstep) { ingest_range(w * w, nT + nL, t0, tstep); };
+  auto ingest_rest = [&](int t0, int tstep) { if (!ABL(64)) ingest_range(w * w, nT + nL, t0, tstep); };
   // ---- panel factorisation, step 1: the pivot block (w <= 16 bus blocks = at most 32 x 32 scalars) is
   // factored entirely in the registers of warp 0: lane = scalar column, a[i] = scalar row i of that
   // column; per 2x2 pivot the inverse is formed once, the two pivot rows are scaled in place
@@ -856,7 +872,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
     // Each step every lane stores its two pivot-row entries: scaled U' right of the pivot, the (already
     // final) multipliers left of it.
 #pragma unroll 1
-    for (int p = 0; p < w; ++p) {
+    for (int p = 0; p < (ABL(512) ? 0 : w); ++p) {
       const int l0 = 2 * p, l1 = 2 * p + 1;
       __syncwarp(full);      // lanes may still be diverged after the data-dependent ingest loops / predicated stores
       const double p00 = __shfl_sync(full, a[0], l0, SW), p01 = __shfl_sync(full, a[0], l1, SW);
@@ -913,7 +929,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
   {
     constexpr int TP = G < 32 ? G : 32;             // task padding: a warp (or lane group) never mixes task kinds
     const int hpad = (h + 1 + TP - 1) & ~(TP - 1);  // column tasks: h structure columns + the rhs
-    for (int t = tid; t < 2 * hpad; t += G) {
+    for (int t = tid; t < (ABL(128) ? 0 : 2 * hpad); t += G) {
       if (t < hpad) {
         const int b = t;
         if (b < h) {
@@ -962,7 +978,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
   // ---- store U' panel and y'
   {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
-    for (int i = tid; i < nT; i += G) stg_blk(U + 2 * i, T0[i], T1[i]);
+    for (int i = tid; i < (ABL(256) ? 0 : nT); i += G) stg_blk(U + 2 * i, T0[i], T1[i]);
     double2* y = A.yv + (size_t)slot * M.m + P.first;
     for (int p = tid; p < w; p += G) y[p] = b1[p];
   }
@@ -994,7 +1010,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
       const double2* u1p = T1 + w + cA;
       const int dB = cB - cA;
 #pragma unroll 2
-      for (int p = 0; p < w; ++p) {
+      for (int p = 0; p < (ABL(8) ? 0 : w); ++p) {
         const double2 ua0 = u0p[p * nf], ua1 = u1p[p * nf];
         const double2 ub0 = u0p[p * nf + dB], ub1 = u1p[p * nf + dB];
 #pragma unroll
@@ -1004,7 +1020,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
           bmsub(acc[i][1][0], acc[i][1][1], l0, l1, ub0, ub1);
         }
       }
-      for (int ci = 0; ci < P.nchild; ++ci) {
+      for (int ci = 0; ci < (ABL(16) ? 0 : (int)P.nchild); ++ci) {
         const ChildDev Cd = M.childdev[P.child_ptr + ci];
         const int hc = Cd.hc;
         const int* inv = M.inv + Cd.inv_off;
@@ -1034,6 +1050,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (a0 + i >= h) break;
+        if (ABL(32) && acc[i][0][0].x != 123.456) continue;       // keep the accumulators live without storing
         if (vA) stg_blk(Co + 2 * ((a0 + i) * h + bA), acc[i][0][0], acc[i][0][1]);
         if (vB) stg_blk(Co + 2 * ((a0 + i) * h + bB), acc[i][1][0], acc[i][1][1]);
       }

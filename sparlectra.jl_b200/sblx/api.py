@@ -581,7 +581,13 @@ def runContingenciesBatched(grid, cases, vm_min_pu=0.9, vm_max_pu=1.1, maxIte=30
             eng.close()
             eng = mk(a2)                                          # Vset may differ for a flat start
         eng.set_v0(a2.v0)
-        idx = [_resolve_branch(grid, c.element) for c in cases]
+        first_by_name = {}
+        for k, nm in enumerate(grid.br_name):
+            first_by_name.setdefault(nm, k)               # _resolve_contingency_branch takes the first match by name
+
+        def resolve(el):
+            return _resolve_branch(grid, el) if "#" in el else first_by_name.get(el)
+        idx = [resolve(c.element) for c in cases]
         lists = [[k] if k is not None else [-1] for k in idx]
         raw = _solve_with_lists(eng, lists, return_raw)
         viol, over = _group(raw["violations"], len(cases)), _group(raw["overloads"], len(cases))

@@ -251,8 +251,8 @@ def test_run_contingencies_batched_names_from_device_lists():
     """runContingenciesBatched no longer pulls V: names come from the device lists; compare with the oracle."""
     g = G.tiled_grid(rows=9, cols=9, augment=True, pv_every=3, pv_q_mvar=24.0, rating_mva=3.0)
     cases = api.generateN1Branches(g)
-    res = api.runContingenciesBatched(g, cases, vm_min_pu=0.99, vm_max_pu=1.02)
-    oracle = O.run_contingencies(g, [[k] for k in range(g.nbranch)], vm_min=0.99, vm_max=1.02)
+    res = api.runContingenciesBatched(g, cases, vm_min_pu=0.99, vm_max_pu=1.015)   # not 1.02: PV buses sit ON their 1.02 setpoint
+    oracle = O.run_contingencies(g, [[k] for k in range(g.nbranch)], vm_min=0.99, vm_max=1.015)
     assert len(res) == len(oracle)
     some = 0
     for r, o in zip(res, oracle):
