@@ -250,6 +250,8 @@ def main():
     vm, va = np.abs(Vb), np.degrees(np.angle(Vb))
     a = M.build_arrays(g, vm=vm, va_deg=va)
     eng.set_v0(a.v0)
+    if os.environ.get("SBLX_MODE_AFTER_BASE"):        # tuning probes: switch an experiment on after the base solve
+        eng.lib.sblx_debug_set_pf_mode(eng.h, int(os.environ["SBLX_MODE_AFTER_BASE"]))
     lo, hi = shard.shard_range(total, rank, world)
     if world > 1 and not sweep:
         uid = [eng.comm_unique_id() if rank == 0 else None]

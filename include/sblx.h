@@ -317,6 +317,10 @@ int sblx_debug_topology(int64_t n, int64_t slack_idx, const uint8_t* bus_type, i
                         const int32_t* outage_ptr, const int32_t* outage_branch, int32_t* island_count, int32_t* status,
                         int32_t* n_isolated);
 
+/* Tuning probe (tools only): sets the k_front prefetch / phase-ablation mode bits (SBLX_PF_MODE) on a live handle, so
+ * that a probe can solve the base case normally and switch the experiment on afterwards. */
+int sblx_debug_set_pf_mode(sblx_handle* h, int32_t mode);
+
 /* Instrumentation: per size class (5) x phase (10) cycle sums of k_front, thread 0's view; only filled by a build with
  * -DSBLX_PHASE_TIMING (tools/phase_timing.py), SBLX_E_ARG otherwise.  `out50` receives 50 doubles. */
 int sblx_debug_phase_cycles(double* out50);

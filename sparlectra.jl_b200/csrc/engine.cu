@@ -2102,6 +2102,15 @@ int sblx_solve_one(sblx_handle* h, const double* v_start, double* v_out, uint8_t
   API_END(h)
 }
 
+int sblx_debug_set_pf_mode(sblx_handle* h, int32_t mode) {
+  if (!h) return SBLX_E_ARG;
+  API_BEGIN(h)
+  h->M.pf_mode = mode;
+  for (auto& lv : h->front_groups)
+    for (auto& g : lv) g.pf_delta = -1;
+  API_END(h)
+}
+
 int sblx_debug_phase_cycles(double* out50) {
 #ifdef SBLX_PHASE_TIMING
   unsigned long long hbuf[50];

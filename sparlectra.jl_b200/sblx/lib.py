@@ -70,7 +70,7 @@ EXPORTS = [
     "sblx_debug_topology", "sblx_solve_injection_sweep", "sblx_solve_injection_scale", "sblx_sweep_factors",
     "sblx_comm_unique_id", "sblx_comm_init_rank", "sblx_comm_destroy", "sblx_solve_outages_sharded", "sblx_shard_bounds",
     "sblx_create_multi", "sblx_destroy_multi", "sblx_multi_last_error", "sblx_multi_set_v0", "sblx_multi_set_locked_pv",
-    "sblx_multi_solve_outages", "sblx_multi_get_stats", "sblx_multi_handle",
+    "sblx_multi_solve_outages", "sblx_multi_get_stats", "sblx_multi_handle", "sblx_debug_set_pf_mode",
 ]
 
 _lib = None
@@ -133,6 +133,7 @@ def load():
     lib.sblx_multi_get_stats.argtypes = [vp, C.c_int32, C.POINTER(Stats)]
     lib.sblx_multi_handle.argtypes = [vp, C.c_int32]
     lib.sblx_multi_handle.restype = vp
+    lib.sblx_debug_set_pf_mode.argtypes = [vp, C.c_int32]
     for name in EXPORTS:
         if getattr(lib, name).restype is C.c_int and name not in ("sblx_version",):
             getattr(lib, name).restype = C.c_int
