@@ -338,3 +338,55 @@ def test_symbolic_selftest_pathological_graphs(name):
         assert levels[2] < 30 < levels[1]          # nested dissection keeps a chain shallow, minimum degree does not
         info, _ = api.analyze_only(Y, 0)           # ... and the automatic choice takes the shallow one
         assert info["ordering"] == "nd"
+
+
+def test_upstream_patch_applies_to_the_reference_tree(tmp_path):
+    """sparlectra.jl_b200/julia/upstream.patch (the :b200 dispatch + extension entries a maintainer adds) must apply
+    cleanly to the reference sources.  /root/reference only exists in the build container: skipped elsewhere."""
+    import shutil, subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("reference tree not present")
+    files = ["Project.toml", "src/solver_interface.jl", "src/contingency.jl", "src/configuration.jl", "src/acpflow/execution.jl",
+             "src/Sparlectra.jl"]
+    for f in files:
+        os.makedirs(os.path.dirname(os.path.join(tmp_path, f)) or tmp_path, exist_ok=True)
+        shutil.copy(os.path.join(ref, f), os.path.join(tmp_path, f))
+    patch = os.path.join(ROOT, "sparlectra.jl_b200", "julia", "upstream.patch")
+    r = subprocess.run(["patch", "-p1", "--dry-run", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    subprocess.check_call(["patch", "-p1", "-s", "-i", patch], cwd=tmp_path)
+    assert ":b200" in open(os.path.join(tmp_path, "src/configuration.jl")).read()
+    assert "SparlectraB200Ext" in open(os.path.join(tmp_path, "Project.toml")).read()
+
+
+def test_julia_struct_layouts_follow_the_header():
+    """LibSblx.jl mirrors sblx_options / sblx_results field by field: same names in the same order as include/sblx.h
+    (the ctypes mirror in sblx/lib.py is checked the same way and its size against the library)."""
+    hdr = open(os.path.join(ROOT, "include", "sblx.h")).read()
+    jl = open(os.path.join(ROOT, "sparlectra.jl_b200", "julia", "LibSblx", "src", "LibSblx.jl")).read()
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1] if " " in decl else decl
+            for nm in names.split(","):
+                out.append(re.sub(r"\[.*\]", "", nm.replace("*", "").strip().split()[-1]))
+        return out
+
+    def jl_fields(struct):
+        body = re.search(r"struct %s\n(.*?)\nend" % struct, jl, re.S).group(1)
+        return [ln.strip().split("::")[0] for ln in body.splitlines() if "::" in ln]
+
+    assert jl_fields("Options") == c_fields("sblx_options")
+    assert jl_fields("Results") == c_fields("sblx_results")
+    from sblx import lib as L
+    assert [f for f, _ in L.Options._fields_] == c_fields("sblx_options")
+    assert [f for f, _ in L.Results._fields_] == c_fields("sblx_results")
+    assert [f for f, _ in L.Stats._fields_] == c_fields("sblx_stats")
+    assert [f for f, _ in L.Info._fields_] == c_fields("sblx_info")
