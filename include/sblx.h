@@ -141,6 +141,12 @@ typedef struct sblx_results {
   int32_t* over_branch;          /* [over_capacity] branch id */
   double* over_loading_pct;      /* [over_capacity] its loading */
   int64_t* over_count;           /* [1] */
+  int64_t qlog_capacity;         /* Q-limit event log of all scenarios = net.qLimitLog (src/limits.jl:75-84): one entry per */
+  int32_t* qlog_scenario;        /* [qlog_capacity] PV->PQ switch, sorted by (scenario, iteration, bus) - the reference's push order */
+  int32_t* qlog_iter;            /* [qlog_capacity] NR iteration of the event (1-based) */
+  int32_t* qlog_bus;             /* [qlog_capacity] bus id */
+  int32_t* qlog_side;            /* [qlog_capacity] +1 = :max, -1 = :min */
+  int64_t* qlog_count;           /* [1] total entries (may exceed the capacity, see above) */
   double* flows;                 /* [B*nbranch*4] per branch S_from (re,im), S_to (re,im) in p.u. (calcNetLosses!,
                                     src/losses.jl:53-85); zero for outaged / out-of-service branches and for
                                     scenarios that did not converge.  Optional and large: B*nbranch*32 bytes */

@@ -537,6 +537,7 @@ class NRResult:
     n_events: int
     numerical_converged: bool
     S: np.ndarray
+    log: list = field(default_factory=list)      # net.qLimitLog: (iteration, bus, side) in push order
 
 
 def run_nr(Y, V0, S0, types0, vset, slack, qmin, qmax, qload, *, maxiter=30, tol=1e-8, damp=1.0,
@@ -643,7 +644,7 @@ def run_nr(Y, V0, S0, types0, vset, slack, qmin, qmax, qload, *, maxiter=30, tol
             converged = False
             reason = R_MAX_SWITCHING                                 # :1027-1036
     return NRResult(V=V, converged=converged, iters=iters, reason=reason, types=types, history=history,
-                    n_events=len(st.log), numerical_converged=numerical, S=S)
+                    n_events=len(st.log), numerical_converged=numerical, S=S, log=list(st.log))
 
 
 # ---------------------------------------------------------------------------
@@ -660,6 +661,7 @@ class PFResult:
     n_events: int
     final_mismatch: float
     iso: list
+    log: list = field(default_factory=list)      # Q-limit events (iteration, bus, side), single-solve path only
 
 
 def runpf(grid, vm, va_deg, removed=(), *, maxiter=30, tol=1e-8, damp=1.0, qlimits_enabled=True,
@@ -706,7 +708,7 @@ def runpf(grid, vm, va_deg, removed=(), *, maxiter=30, tol=1e-8, damp=1.0, qlimi
         for i in iso:
             tt[i] = ISO
         return PFResult(r.converged, r.iters, r.reason, r.V, tt, len(comps), r.n_events,
-                        r.history[-1] if r.history else float("nan"), iso)
+                        r.history[-1] if r.history else float("nan"), iso, log=r.log)
     # multi-island path (:1919-2243): validate references, solve each island with branches
     refs = []
     for comp in comps:

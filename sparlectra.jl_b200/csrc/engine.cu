@@ -401,7 +401,7 @@ static void nccl_destroy(ncclComm_t c) {
 // what the caller wants back besides the per-scenario summary
 struct Want {
   bool v = false, types = false, flows = false;
-  int64_t viol_cap = 0, over_cap = 0;
+  int64_t viol_cap = 0, over_cap = 0, qlog_cap = 0;
 };
 
 }  // namespace sblx
@@ -441,7 +441,7 @@ struct sblx_handle {
   DevBuf<unsigned char> s_type, s_iso, s_evcnt, s_evact;
   DevBuf<short> s_evlast;
   DevBuf<int> s_scen, s_iter, s_state, s_changed, s_nev, s_singular, s_numerical, s_reason, s_viol, s_maxsw, s_rated, s_out_cnt, s_out_br;
-  DevBuf<int> s_nvv, s_nov, s_tiny;
+  DevBuf<int> s_nvv, s_nov, s_tiny, s_tinyit;
   DevBuf<unsigned long long> s_mis, s_mis2, s_pvres, s_vminb, s_vmaxb, s_loadb;
   DevBuf<int> l_active, l_fresh, l_step, l_fin, l_counts;
   Slots A{};
@@ -457,6 +457,8 @@ struct sblx_handle {
   DevBuf<double> r_fm, r_vmin, r_vmax, r_load, r_over_pct;
   DevBuf<double2> r_V, r_flows;
   DevBuf<int2> r_viol_list, r_over_list;
+  DevBuf<int4> r_qlog_list;
+  int64_t qlog_cap = 0;
   DevBuf<unsigned long long> r_list_counts;
   DevBuf<unsigned char> r_types;
   DevBuf<SummaryRec> r_summary, g_summary;     // own records (padded to the common shard size) / gathered records of all ranks
@@ -741,7 +743,7 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   h->s_scen.alloc(W); h->s_iter.alloc(W); h->s_state.alloc(W); h->s_changed.alloc(W); h->s_nev.alloc(W);
   h->s_singular.alloc(W); h->s_numerical.alloc(W); h->s_reason.alloc(W); h->s_viol.alloc(W); h->s_maxsw.alloc(W);
   h->s_rated.alloc(W); h->s_out_cnt.alloc(W); h->s_out_br.alloc((size_t)W * MAXOUT); h->s_fm.alloc(W);
-  h->s_nvv.alloc(W); h->s_nov.alloc(W); h->s_tiny.alloc(W);
+  h->s_nvv.alloc(W); h->s_nov.alloc(W); h->s_tiny.alloc(W); h->s_tinyit.alloc(W);
   h->s_mis.alloc(W); h->s_mis2.alloc(W); h->s_pvres.alloc(W); h->s_vminb.alloc(W); h->s_vmaxb.alloc(W); h->s_loadb.alloc(W);
   h->l_active.alloc(W); h->l_fresh.alloc(W); h->l_step.alloc(W); h->l_fin.alloc(W); h->l_counts.alloc(8);
   h->W = (int)W;
@@ -756,7 +758,7 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   A.mis_bits = h->s_mis.p; A.mis2_bits = h->s_mis2.p; A.fm = h->s_fm.p;
   A.pvres_bits = h->s_pvres.p; A.vmin_bits = h->s_vminb.p; A.vmax_bits = h->s_vmaxb.p; A.load_bits = h->s_loadb.p;
   A.viol = h->s_viol.p; A.maxsw = h->s_maxsw.p; A.rated = h->s_rated.p; A.out_cnt = h->s_out_cnt.p; A.out_br = h->s_out_br.p;
-  A.nvv = h->s_nvv.p; A.nov = h->s_nov.p; A.tiny = h->s_tiny.p;
+  A.nvv = h->s_nvv.p; A.nov = h->s_nov.p; A.tiny = h->s_tiny.p; A.tinyit = h->s_tinyit.p;
   Lists& L = h->L;
   L.active = h->l_active.p; L.fresh = h->l_fresh.p; L.step = h->l_step.p; L.fin = h->l_fin.p; L.counts = h->l_counts.p;
 }
@@ -920,8 +922,10 @@ static void alloc_results(sblx_handle* h, int64_t B, const Want& want) {
   h->viol_cap = want.viol_cap; h->over_cap = want.over_cap;
   if (want.viol_cap > 0) h->r_viol_list.alloc(want.viol_cap); else h->r_viol_list.release();
   if (want.over_cap > 0) { h->r_over_list.alloc(want.over_cap); h->r_over_pct.alloc(want.over_cap); } else { h->r_over_list.release(); h->r_over_pct.release(); }
-  h->r_list_counts.alloc(2);
-  CK(cudaMemsetAsync(h->r_list_counts.p, 0, 2 * sizeof(unsigned long long), h->stream));
+  h->qlog_cap = want.qlog_cap;
+  if (want.qlog_cap > 0) h->r_qlog_list.alloc(want.qlog_cap); else h->r_qlog_list.release();
+  h->r_list_counts.alloc(4);
+  CK(cudaMemsetAsync(h->r_list_counts.p, 0, 4 * sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->r_nvv.p, 0, B * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->r_nov.p, 0, B * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->r_tiny.p, 0, B * sizeof(int), h->stream));
@@ -953,6 +957,7 @@ static void set_batch(sblx_handle* h) {
   Bt.r_nvv = h->r_nvv.p; Bt.r_nov = h->r_nov.p; Bt.r_tiny = h->r_tiny.p;
   Bt.viol_list = h->r_viol_list.p; Bt.over_list = h->r_over_list.p; Bt.over_pct = h->r_over_pct.p;
   Bt.list_counts = h->r_list_counts.p; Bt.viol_cap = h->viol_cap; Bt.over_cap = h->over_cap;
+  Bt.qlog_list = h->r_qlog_list.p; Bt.qlog_cap = h->qlog_cap;
   Bt.r_flows = h->r_flows.p;
   Bt.r_conv = h->r_conv.p; Bt.r_status = h->r_status.p; Bt.r_iter = h->r_iter.p; Bt.r_nsw = h->r_nsw.p;
   Bt.r_fm = h->r_fm.p; Bt.r_vmin = h->r_vmin.p; Bt.r_vmax = h->r_vmax.p; Bt.r_load = h->r_load.p;
@@ -1279,6 +1284,10 @@ static void run_staged(sblx_handle* h) {
     }
     CK(cudaEventRecord(ev[6], s));
     if (nstep > 0) {
+      if (h->M.pivot_tol > 0.0) {
+        k_tiny_guard<<<nstep, 256, 0, s>>>(h->M, h->A, h->L);
+        st.launches++;
+      }
       dim3 g((m + 7) / 8, (nstep + 31) / 32);
       k_update<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
       k_poststep<<<(nstep + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L);
@@ -1331,6 +1340,7 @@ static Want want_from(const sblx_results* res) {
   w.flows = res->flows != nullptr;
   w.viol_cap = (res->viol_scenario && res->viol_bus && res->viol_capacity > 0) ? res->viol_capacity : 0;
   w.over_cap = (res->over_scenario && res->over_branch && res->over_capacity > 0) ? res->over_capacity : 0;
+  w.qlog_cap = (res->qlog_scenario && res->qlog_iter && res->qlog_bus && res->qlog_side && res->qlog_capacity > 0) ? res->qlog_capacity : 0;
   return w;
 }
 
@@ -1390,11 +1400,13 @@ static void fetch_results(sblx_handle* h, sblx_results* res, int64_t dst0 = 0, b
     if (nsub > 0) { subF.resize((size_t)nsub * nbr * 2); CK(cudaMemcpyAsync(subF.data(), h->r_flows.p + (size_t)B * nbr * 2, (size_t)nsub * nbr * 32, cudaMemcpyDeviceToHost, s)); }
   }
   // compacted violation / overload lists
-  unsigned long long lc[2] = {0, 0};
+  unsigned long long lc[4] = {0, 0, 0, 0};
   std::vector<int2> vl, ol;
+  std::vector<int4> ql;
   std::vector<double> op;
   const bool wantVL = h->viol_cap > 0 && res->viol_scenario, wantOL = h->over_cap > 0 && res->over_scenario;
-  if (wantVL || wantOL) {
+  const bool wantQL = h->qlog_cap > 0 && res->qlog_scenario;
+  if (wantVL || wantOL || wantQL) {
     CK(cudaMemcpyAsync(lc, h->r_list_counts.p, sizeof lc, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (wantVL) {
@@ -1409,7 +1421,11 @@ static void fetch_results(sblx_handle* h, sblx_results* res, int64_t dst0 = 0, b
         CK(cudaMemcpyAsync(op.data(), h->r_over_pct.p, ol.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
       }
     }
-    bytes += (int64_t)(vl.size() * 8 + ol.size() * 16);
+    if (wantQL) {
+      ql.resize((size_t)std::min<unsigned long long>(lc[2], (unsigned long long)h->qlog_cap));
+      if (!ql.empty()) CK(cudaMemcpyAsync(ql.data(), h->r_qlog_list.p, ql.size() * sizeof(int4), cudaMemcpyDeviceToHost, s));
+    }
+    bytes += (int64_t)(vl.size() * 8 + ol.size() * 16 + ql.size() * 16);
   }
   CK(cudaStreamSynchronize(s));
   if (summary) fill_summary(res, recs.data(), B, dst0);
@@ -1463,6 +1479,26 @@ static void fetch_results(sblx_handle* h, sblx_results* res, int64_t dst0 = 0, b
   };
   if (wantVL) finish_list(vl, nullptr, lc[0], h->viol_cap, res->viol_scenario, res->viol_bus, nullptr, res->viol_count);
   if (wantOL) finish_list(ol, &op, lc[1], h->over_cap, res->over_scenario, res->over_branch, res->over_loading_pct, res->over_count);
+  if (wantQL) {
+    // the event log of EVERY solved scenario (converged or not), island sub-scenarios under their caller scenario;
+    // order = the reference's push order: by iteration, buses ascending within an iteration (limits.jl:439-524)
+    std::vector<int4> keep;
+    keep.reserve(ql.size());
+    for (int4 e : ql) {
+      if (e.x >= B) e.x = (e.x - B) < (int64_t)R.parent.size() ? R.parent[e.x - B] : -1;
+      if (e.x >= 0) keep.push_back(e);
+    }
+    std::stable_sort(keep.begin(), keep.end(), [](const int4& a, const int4& b) {
+      return a.x != b.x ? a.x < b.x : a.y != b.y ? a.y < b.y : a.z < b.z;
+    });
+    for (size_t j = 0; j < keep.size() && (int64_t)j < h->qlog_cap; ++j) {
+      res->qlog_scenario[j] = (int32_t)(keep[j].x + dst0);
+      res->qlog_iter[j] = keep[j].y;
+      res->qlog_bus[j] = keep[j].z + base;
+      res->qlog_side[j] = keep[j].w;
+    }
+    if (res->qlog_count) *res->qlog_count = lc[2] > (unsigned long long)h->qlog_cap ? (int64_t)lc[2] : (int64_t)keep.size();
+  }
   h->stats.d2h_ms = now_ms() - t0;
   h->stats.d2h_bytes = bytes;
 }
@@ -1941,12 +1977,18 @@ int sblx_multi_solve_outages(sblx_multi* m, int64_t B, const int32_t* outage_ptr
   }
   const int nd = (int)m->hs.size();
   // per-rank list buffers (the ranks append concurrently; merged in rank = input order afterwards)
-  struct RankLists { std::vector<int32_t> vs, vb, os, ob; std::vector<double> op; int64_t vc = 0, oc = 0; };
+  struct RankLists { std::vector<int32_t> vs, vb, os, ob, qs, qi, qb, qd; std::vector<double> op; int64_t vc = 0, oc = 0, qc = 0; };
   std::vector<RankLists> rl(nd);
   std::vector<sblx_results> rr(nd, *res);
   const bool wantVL = res->viol_scenario && res->viol_bus && res->viol_capacity > 0;
   const bool wantOL = res->over_scenario && res->over_branch && res->over_capacity > 0;
+  const bool wantQL = res->qlog_scenario && res->qlog_iter && res->qlog_bus && res->qlog_side && res->qlog_capacity > 0;
   for (int i = 0; i < nd; ++i) {
+    if (wantQL) {
+      rl[i].qs.resize(res->qlog_capacity); rl[i].qi.resize(res->qlog_capacity); rl[i].qb.resize(res->qlog_capacity); rl[i].qd.resize(res->qlog_capacity);
+      rr[i].qlog_scenario = rl[i].qs.data(); rr[i].qlog_iter = rl[i].qi.data(); rr[i].qlog_bus = rl[i].qb.data(); rr[i].qlog_side = rl[i].qd.data();
+      rr[i].qlog_count = &rl[i].qc;
+    }
     if (wantVL) { rl[i].vs.resize(res->viol_capacity); rl[i].vb.resize(res->viol_capacity); rr[i].viol_scenario = rl[i].vs.data(); rr[i].viol_bus = rl[i].vb.data(); rr[i].viol_count = &rl[i].vc; }
     if (wantOL) {
       rl[i].os.resize(res->over_capacity); rl[i].ob.resize(res->over_capacity); rl[i].op.resize(res->over_capacity);
@@ -1991,6 +2033,17 @@ int sblx_multi_solve_outages(sblx_multi* m, int64_t B, const int32_t* outage_ptr
       tot += rl[i].oc;
     }
     if (res->over_count) *res->over_count = tot;
+  }
+  if (wantQL) {
+    int64_t tot = 0, w = 0;
+    for (int i = 0; i < nd; ++i) {
+      const int64_t have = std::min<int64_t>(rl[i].qc, res->qlog_capacity);
+      for (int64_t j = 0; j < have && w < res->qlog_capacity; ++j, ++w) {
+        res->qlog_scenario[w] = rl[i].qs[j]; res->qlog_iter[w] = rl[i].qi[j]; res->qlog_bus[w] = rl[i].qb[j]; res->qlog_side[w] = rl[i].qd[j];
+      }
+      tot += rl[i].qc;
+    }
+    if (res->qlog_count) *res->qlog_count = tot;
   }
   return SBLX_OK;
 }

@@ -21,6 +21,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+
+// Bounds-checked build (-DSBLX_BOUNDS_CHECK, tools/sanitize_run.py): compute-sanitizer is closed on the GPU pool, so
+// every symbolic index the factorisation kernels follow is range-checked here instead; a violation traps the kernel
+// (the host call then fails with a CUDA error).  Compiled out of the product build.
+#ifdef SBLX_BOUNDS_CHECK
+#define SBLX_CHECK(cond)                                                                                      \
+  do {                                                                                                        \
+    if (!(cond)) {                                                                                            \
+      printf("SBLX_CHECK failed: %s (%s:%d) block (%d,%d) thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x); \
+      __trap();                                                                                               \
+    }                                                                                                         \
+  } while (0)
+#else
+#define SBLX_CHECK(cond)
+#endif
+
 namespace sblx {
 
 constexpr int ING_NONE = INT32_MIN, ING_MULTI = 1 << 30;   // ingest word encoding (same constants in symbolic.h)
@@ -70,7 +87,7 @@ struct Slots {
   int* scen; int* iter; int* state; int* changed; int* nev; int* singular; int* numerical; int* reason;
   unsigned long long* mis_bits; unsigned long long* mis2_bits; double* fm;
   unsigned long long* pvres_bits; unsigned long long* vmin_bits; unsigned long long* vmax_bits; unsigned long long* load_bits;
-  int* viol; int* maxsw; int* rated; int* nvv; int* nov; int* tiny;   // nvv / nov: voltage-band violations / overloaded branches; tiny: near-singular pivot blocks
+  int* viol; int* maxsw; int* rated; int* nvv; int* nov; int* tiny; int* tinyit;   // nvv / nov: voltage-band violations / overloaded branches; tiny: near-singular pivot blocks
   int* out_cnt; int* out_br;   // [W][MAXOUT]
 };
 
@@ -96,6 +113,7 @@ struct Batch {
   int* r_nvv; int* r_nov; int* r_tiny;      // per scenario: voltage-band violations, overloaded branches (contingency.jl:149-178), tiny pivots
   // compacted (scenario, bus) / (scenario, branch) lists, appended with one atomic per entry (order restored on the host)
   int2* viol_list; int2* over_list; double* over_pct; unsigned long long* list_counts; long long viol_cap, over_cap;
+  int4* qlog_list; long long qlog_cap;      // Q-limit event log {scenario, iteration, bus, side (+1 max, -1 min)} = net.qLimitLog (limits.jl:75-84)
   double2* r_flows;            // [B][nbr][2] complex branch flows S_from, S_to in p.u. (losses.jl:53-85), optional
 };
 
@@ -233,6 +251,7 @@ __global__ void __launch_bounds__(1024) k_assign(DevModel M, Slots A, Lists L, B
       A.mis_bits[slot] = 0ull;
       A.mis2_bits[slot] = 0ull;
       A.changed[slot] = 0;
+      A.tinyit[slot] = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) s_nact = na + s_total;
@@ -356,6 +375,7 @@ __global__ void __launch_bounds__(256) k_mismatch(DevModel M, Slots A, Lists L) 
     if (!A.iso[k]) {
       for (int p = M.y_rowptr[bus]; p < M.y_rowptr[bus + 1]; ++p) {
         const double2 y = M.y_val[p];
+        SBLX_CHECK(M.y_col[p] >= 0 && M.y_col[p] < M.n && slot >= 0 && slot < M.W);
         const double2 v = A.V[(size_t)M.y_col[p] * W + slot];
         I.x += y.x * v.x - y.y * v.y;
         I.y += y.x * v.y + y.y * v.x;
@@ -444,6 +464,10 @@ __global__ void __launch_bounds__(256) k_qlimit(DevModel M, Slots A, Lists L, Ba
       atomicAdd(&A.nev[slot], 1);
       atomicOr(&A.changed[slot], 1);
       touched = true;
+      if (Bt.qlog_list) {
+        const unsigned long long q = atomicAdd(&Bt.list_counts[2], 1ull);
+        if ((long long)q < Bt.qlog_cap) Bt.qlog_list[q] = make_int4(scen, it, bus, side);
+      }
     }
   }
   if (M.allow_reenable && type != T_PV && A.evact[k] && A.evcnt[k] <= 1) {    // limits.jl:527-561
@@ -557,6 +581,7 @@ __global__ void __launch_bounds__(256) k_jacobian(DevModel M, Slots A, Lists L) 
     const int e = threadIdx.y + 8 * q, ent = ent0 + e;
     if (!live || ent >= M.nnzB) continue;
     const int i = M.bus_of_node[M.jb_row[ent]], j = M.bus_of_node[M.jb_col[ent]];
+    SBLX_CHECK(i >= 0 && i < M.n && j >= 0 && j < M.n && M.jb_ypos[ent] >= 0 && slot >= 0 && slot < M.W);
     const size_t ki = (size_t)i * W + slot;
     double b00 = 0, b01 = 0, b10 = 0, b11 = 0;
     const bool isoi = A.iso[ki] != 0, isoj = A.iso[(size_t)j * W + slot] != 0;
@@ -791,6 +816,8 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
 #pragma unroll
       for (int i = 0; i < IB; ++i) {
         const int v = e[i].x;
+        SBLX_CHECK(v == ING_NONE || v >= ING_MULTI || (v < 0 ? (~v) < M.nnzB : (long long)v < M.c_blocks));
+        SBLX_CHECK(e[i].y < nT + nL);
         const double2* ptr = v < 0 ? Jv + 2 * (size_t)(~v) : Ca + 2 * (size_t)v;
         x0[i] = make_double2(0.0, 0.0);
         x1[i] = x0[i];
@@ -802,6 +829,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
           const int x = e[i].x - ING_MULTI;
           for (int q = M.ing_xptr[x]; q < M.ing_xptr[x + 1]; ++q) {
             const int sidx = M.ing_xsrc[q];
+            SBLX_CHECK(sidx < 0 ? (~sidx) < M.nnzB : (long long)sidx < M.c_blocks);
             const double2* ptr = sidx < 0 ? Jv + 2 * (size_t)(~sidx) : Ca + 2 * (size_t)sidx;
             double2 s0, s1;
             ldg_blk(ptr, s0, s1);
@@ -823,7 +851,10 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
     const int* vptr = M.vec_ptr + P.first;
     for (int p = tid; p < w; p += G) {
       double2 v = r[p];
-      for (int q = vptr[p]; q < vptr[p + 1]; ++q) v = cadd(v, Ca[M.vec_src[q]]);
+      for (int q = vptr[p]; q < vptr[p + 1]; ++q) {
+        SBLX_CHECK(M.vec_src[q] >= 0 && (long long)M.vec_src[q] < 2 * M.c_blocks);
+        v = cadd(v, Ca[M.vec_src[q]]);
+      }
       b1[p] = v;
     }
   }
@@ -914,7 +945,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
       a[2 * WR - 1] = 0.0;
     }
     if (sing && lane == 0) atomicOr(&A.singular[slot], 1);
-    if (ntiny && lane == 0) atomicAdd(&A.tiny[slot], ntiny);
+    if (ntiny && lane == 0) { atomicAdd(&A.tiny[slot], ntiny); A.tinyit[slot] = 1; }
     PHASE_MARK(1);   // pivot-block chain (warp 0)
     if (NT == 32) ingest_rest(tid, G);
   }
@@ -978,6 +1009,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
   // ---- store U' panel and y'
   {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
+    SBLX_CHECK(P.u_off >= 0 && P.u_off + nT <= M.u_blocks && P.first >= 0 && P.first + w <= M.m && slot >= 0 && slot < M.W);
     for (int i = tid; i < (ABL(256) ? 0 : nT); i += G) stg_blk(U + 2 * i, T0[i], T1[i]);
     double2* y = A.yv + (size_t)slot * M.m + P.first;
     for (int p = tid; p < w; p += G) y[p] = b1[p];
@@ -985,6 +1017,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
   PHASE_MARK(4);   // U store issue
   if (h == 0) return;
   double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
+  SBLX_CHECK(P.c_off >= 0 && P.c_off + (long long)h * h + (h + 1) / 2 <= M.c_blocks);
   // ---- Schur complement straight to HBM: C = gather(children) - L * U'
   if (NT >= 128) {
     // warp-level work items: 4 structure rows x 64 structure columns; lane l owns columns (cg*64 + l) and
@@ -1026,6 +1059,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
         const int* inv = M.inv + Cd.inv_off;
         const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
         const int ibA = vA ? inv[bA] : -1, ibB = vB ? inv[bB] : -1;
+        SBLX_CHECK(ibA < hc && ibB < hc && Cd.c_off >= 0 && Cd.c_off + (long long)hc * hc <= M.c_blocks);
         // all (predicated) loads are issued before any accumulation: 16 independent 16 B loads in flight
         double2 g[4][2][2];
         int ia[4];
@@ -1033,6 +1067,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
         for (int i = 0; i < 4; ++i) ia[i] = (a0 + i < h) ? inv[a0 + i] : -1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          SBLX_CHECK(ia[i] < hc);
           const bool okA = ia[i] >= 0 && ibA >= 0, okB = ia[i] >= 0 && ibB >= 0;
           const double2* spA = Cm + 2 * ((size_t)(okA ? ia[i] : 0) * hc + (okA ? ibA : 0));
           const double2* spB = Cm + 2 * ((size_t)(okB ? ia[i] : 0) * hc + (okB ? ibB : 0));
@@ -1084,6 +1119,7 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
         const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
         const int ia0 = inv[a0], ia1 = va ? inv[a0 + 1] : -1;
         const int ib0 = inv[b0], ib1 = vb ? inv[b0 + 1] : -1;
+        SBLX_CHECK(ia0 < hc && ia1 < hc && ib0 < hc && ib1 < hc && Cd.c_off >= 0 && Cd.c_off + (long long)hc * hc <= M.c_blocks);
         if (ia0 >= 0 && ib0 >= 0) { double2 s0, s1; ldg_blk(Cm + 2 * (ia0 * hc + ib0), s0, s1); acc[0][0][0] = cadd(acc[0][0][0], s0); acc[0][0][1] = cadd(acc[0][0][1], s1); }
         if (ia0 >= 0 && ib1 >= 0) { double2 s0, s1; ldg_blk(Cm + 2 * (ia0 * hc + ib1), s0, s1); acc[0][1][0] = cadd(acc[0][1][0], s0); acc[0][1][1] = cadd(acc[0][1][1], s1); }
         if (ia1 >= 0 && ib0 >= 0) { double2 s0, s1; ldg_blk(Cm + 2 * (ia1 * hc + ib0), s0, s1); acc[1][0][0] = cadd(acc[1][0][0], s0); acc[1][0][1] = cadd(acc[1][0][1], s1); }
@@ -1159,6 +1195,7 @@ __global__ void __launch_bounds__(32, (NF <= 8 ? 16 : 10)) k_front_reg(DevModel 
     a1[c] = a0[c];
     if (c < nf && mine) {
       const int v = words[c];
+      SBLX_CHECK(v == ING_NONE || v >= ING_MULTI || (v < 0 ? (~v) < M.nnzB : (long long)v < M.c_blocks));
       if (v != ING_NONE) {
         if (v < ING_MULTI) {
           ldg_blk(v < 0 ? Jv + 2 * (size_t)(~v) : Ca + 2 * (size_t)v, a0[c], a1[c]);
@@ -1223,7 +1260,7 @@ __global__ void __launch_bounds__(32, (NF <= 8 ? 16 : 10)) k_front_reg(DevModel 
     }
   }
   if (sing && r == 0) atomicOr(&A.singular[slot], 1);
-  if (ntiny && r == 0) atomicAdd(&A.tiny[slot], ntiny);
+  if (ntiny && r == 0) { atomicAdd(&A.tiny[slot], ntiny); A.tinyit[slot] = 1; }
   // ---- outputs: U' rows and y' of the pivots, update matrix + update vector of the structure rows
   if (r < w) {
     double2* U = reinterpret_cast<double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4) + 2 * (size_t)(r * nf);
@@ -1578,7 +1615,10 @@ __global__ void __launch_bounds__(NT) k_backsolve(DevModel M, Slots A, Lists L, 
   const double2* U = reinterpret_cast<const double2*>(A.U + ((size_t)slot * M.u_blocks + P.u_off) * 4);
   const double2* y = A.yv + (size_t)slot * M.m + P.first;
   const int* sn = M.struct_nodes + P.struct_ptr;
-  for (int b = tid; b < h; b += NT) xs[b] = xv[sn[b]];
+  for (int b = tid; b < h; b += NT) {
+    SBLX_CHECK(sn[b] >= 0 && sn[b] < M.m);
+    xs[b] = xv[sn[b]];
+  }
   // the strictly upper part of the pivot block goes to shared memory now: the serial back substitution below must
   // not pay one HBM round trip per pivot
   double2* Ub = t + w;      // [w*w][2]
@@ -1650,6 +1690,7 @@ __global__ void __launch_bounds__(32) k_backsolve_small(DevModel M, Slots A, Lis
     for (int b = 0; b < h; ++b) {
       double2 u0, u1;
       ldg_blk(row + 2 * b, u0, u1);
+      SBLX_CHECK(sn[b] >= 0 && sn[b] < M.m);
       const double2 x = xv[sn[b]];
       r.x -= u0.x * x.x + u0.y * x.y;
       r.y -= u1.x * x.x + u1.y * x.y;
@@ -1665,6 +1706,51 @@ __global__ void __launch_bounds__(32) k_backsolve_small(DevModel M, Slots A, Lis
     }
   }
   if (p < w) xv[P.first + p] = r;
+}
+
+// Safety net of the static-pivoting LU (the reference's UMFPACK pivots across rows and falls back to QR / SVD,
+// solver_core.jl:60-82): a factorisation that met a tiny pivot block re-checks its own solve.  One CTA per stepping
+// scenario, immediately out unless the scenario was flagged in THIS iteration: r = (-F) - J dx with the stored
+// Jacobian blocks (scratch: the y vector, dead after the back substitution); a step whose residual exceeds
+// 1e-6 |F|_inf is not applied - the scenario ends as singular_newton_step instead of silently taking a bad step.
+__global__ void __launch_bounds__(256) k_tiny_guard(DevModel M, Slots A, Lists L) {
+  __shared__ double red[2][256];
+  if ((int)blockIdx.x >= L.counts[2]) return;
+  const int slot = L.step[blockIdx.x];
+  if (!A.tinyit[slot] || A.singular[slot]) return;
+  double2* r = A.yv + (size_t)slot * M.m;
+  const double2* rhs = A.rhs + (size_t)slot * M.m;
+  const double2* x = A.xv + (size_t)slot * M.m;
+  const double* Jv = A.Jv + (size_t)slot * M.nnzB * 4;
+  for (int e = threadIdx.x; e < M.m; e += 256) r[e] = rhs[e];
+  __syncthreads();
+  for (int k = threadIdx.x; k < M.nnzB; k += 256) {
+    const int er = M.elim_of_node[M.jb_row[k]], ec = M.elim_of_node[M.jb_col[k]];
+    const double2 xc = x[ec];
+    const double* b = Jv + 4 * (size_t)k;
+    atomicAdd(&r[er].x, -(b[0] * xc.x + b[1] * xc.y));
+    atomicAdd(&r[er].y, -(b[2] * xc.x + b[3] * xc.y));
+  }
+  __syncthreads();
+  double mr = 0.0, mf = 0.0;
+  bool bad = false;
+  for (int e = threadIdx.x; e < M.m; e += 256) {
+    const double2 a = r[e], f = rhs[e];
+    bad |= !(isfinite(a.x) && isfinite(a.y));
+    mr = fmax(mr, fmax(fabs(a.x), fabs(a.y)));
+    mf = fmax(mf, fmax(fabs(f.x), fabs(f.y)));
+  }
+  red[0][threadIdx.x] = bad ? INFINITY : mr;
+  red[1][threadIdx.x] = mf;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if ((int)threadIdx.x < s2) {
+      red[0][threadIdx.x] = fmax(red[0][threadIdx.x], red[0][threadIdx.x + s2]);
+      red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + s2]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && !(red[0][0] <= 1e-6 * fmax(red[1][0], 1e-300))) A.singular[slot] = 1;
 }
 
 // V += damp * dx (slack untouched).  grid (ceil(m/8), ceil(nStep/32)), block (32, 8)
@@ -1722,6 +1808,7 @@ __global__ void __launch_bounds__(256) k_fin_bus(DevModel M, Slots A, Lists L, B
   const double2 V = A.V[k];
   const int type = A.type[k];
   const bool iso = A.iso[k] != 0;
+  SBLX_CHECK(scen >= 0 && scen < Bt.B);
   if (Bt.r_V) Bt.r_V[(size_t)scen * M.n + bus] = V;
   if (Bt.r_types) Bt.r_types[(size_t)scen * M.n + bus] = (unsigned char)(iso ? T_ISO : type);
   if (!A.numerical[slot]) return;

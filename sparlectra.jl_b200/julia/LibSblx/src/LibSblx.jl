@@ -61,6 +61,12 @@ struct Results
   over_branch::Ptr{Int32}
   over_loading_pct::Ptr{Float64}
   over_count::Ptr{Int64}
+  qlog_capacity::Int64
+  qlog_scenario::Ptr{Int32}
+  qlog_iter::Ptr{Int32}
+  qlog_bus::Ptr{Int32}
+  qlog_side::Ptr{Int32}
+  qlog_count::Ptr{Int64}
   flows::Ptr{Float64}
 end
 
@@ -178,7 +184,8 @@ function solve_outages(h::Handle, cases::Vector{Vector{Int}}; want_v::Bool = fal
     res = Results(pointer(conv), pointer(st), pointer(it), pointer(nsw), pointer(isl), pointer(fm), pointer(vmin), pointer(vmax), pointer(ld),
                   want_v ? Ptr{Float64}(pointer(V)) : Ptr{Float64}(C_NULL), Ptr{UInt8}(C_NULL), pointer(nvv), pointer(nov), pointer(ntp),
                   cap, pointer(vs), pointer(vb), Base.unsafe_convert(Ptr{Int64}, vc), cap, pointer(os), pointer(ob), pointer(op),
-                  Base.unsafe_convert(Ptr{Int64}, oc), Ptr{Float64}(C_NULL))
+                  Base.unsafe_convert(Ptr{Int64}, oc), 0, Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL),
+                  Ptr{Int64}(C_NULL), Ptr{Float64}(C_NULL))
     GC.@preserve vc oc begin
       if h.multi
         check_multi(ccall((:sblx_multi_solve_outages, libsblx), Cint, (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Ref{Results}), h.ptr, B, optr, obr, res), h.ptr)

@@ -180,6 +180,8 @@ class Engine:
             r["_over_branch"] = np.zeros(cap, np.int32)
             r["_over_pct"] = np.zeros(cap)
             r["_over_count"] = np.zeros(1, np.int64)
+            r["_qlog"] = [np.zeros(cap, np.int32) for _ in range(4)]
+            r["_qlog_count"] = np.zeros(1, np.int64)
         if want_flows:
             r["flows"] = np.zeros((B, nbranch, 2), np.complex128)
         return r
@@ -211,6 +213,9 @@ class Engine:
             s.over_branch = L.ptr(r["_over_branch"], L.c_i32p)
             s.over_loading_pct = L.ptr(r["_over_pct"], L.c_f64p)
             s.over_count = L.ptr(r["_over_count"], L.c_i64p)
+            s.qlog_capacity = len(r["_qlog"][0])
+            s.qlog_scenario, s.qlog_iter, s.qlog_bus, s.qlog_side = (L.ptr(x, L.c_i32p) for x in r["_qlog"])
+            s.qlog_count = L.ptr(r["_qlog_count"], L.c_i64p)
         s.flows = L.ptr(r["flows"].view(np.float64), L.c_f64p) if "flows" in r else None
         return s
 
@@ -218,8 +223,12 @@ class Engine:
         """trim the compacted (scenario, element) lists to their counts and shift ids back to 0-based"""
         if "_viol_scenario" not in r:
             return r
-        nv, no = int(r["_viol_count"][0]), int(r["_over_count"][0])
-        r["lists_complete"] = nv <= len(r["_viol_scenario"]) and no <= len(r["_over_scenario"])
+        nv, no, nq = int(r["_viol_count"][0]), int(r["_over_count"][0]), int(r["_qlog_count"][0])
+        r["lists_complete"] = nv <= len(r["_viol_scenario"]) and no <= len(r["_over_scenario"]) and nq <= len(r["_qlog"][0])
+        q = r.pop("_qlog")
+        nq = min(nq, len(q[0]))
+        r["qlimit_events"] = np.stack([q[0][:nq], q[1][:nq], q[2][:nq] - self.base, q[3][:nq]], axis=1)   # scenario, iteration, bus, side
+        r["qlimit_event_total"] = int(r.pop("_qlog_count")[0])
         nv, no = min(nv, len(r["_viol_scenario"])), min(no, len(r["_over_scenario"]))
         r["violations"] = np.stack([r.pop("_viol_scenario")[:nv], r.pop("_viol_bus")[:nv] - self.base], axis=1)
         r["overloads"] = np.stack([r.pop("_over_scenario")[:no], r.pop("_over_branch")[:no] - self.base], axis=1)
@@ -539,7 +548,7 @@ def _solve_with_lists(eng, lists, return_raw):
     raw = eng.solve_outages(lists, want_v=return_raw, want_types=return_raw, want_lists=True)
     if not raw["lists_complete"]:
         raw = eng.solve_outages(lists, want_v=return_raw, want_types=return_raw, want_lists=True,
-                                list_capacity=max(raw["violation_total"], raw["overload_total"]) + 16)
+                                list_capacity=max(raw["violation_total"], raw["overload_total"], raw["qlimit_event_total"]) + 16)
     return raw
 
 

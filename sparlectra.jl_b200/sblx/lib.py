@@ -37,7 +37,9 @@ class Results(C.Structure):
         ("n_voltage_violations", c_i32p), ("n_overloaded", c_i32p), ("n_tiny_pivots", c_i32p),
         ("viol_capacity", C.c_int64), ("viol_scenario", c_i32p), ("viol_bus", c_i32p), ("viol_count", c_i64p),
         ("over_capacity", C.c_int64), ("over_scenario", c_i32p), ("over_branch", c_i32p), ("over_loading_pct", c_f64p),
-        ("over_count", c_i64p), ("flows", c_f64p),
+        ("over_count", c_i64p),
+        ("qlog_capacity", C.c_int64), ("qlog_scenario", c_i32p), ("qlog_iter", c_i32p), ("qlog_bus", c_i32p), ("qlog_side", c_i32p),
+        ("qlog_count", c_i64p), ("flows", c_f64p),
     ]
 
 

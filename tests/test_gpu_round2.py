@@ -424,3 +424,21 @@ def test_sharded_solve_two_processes_every_rank_gets_all_records():
         assert nr == 2 and np.array_equal(conv, ref["converged"]) and np.array_equal(it, ref["iterations"])
         assert np.array_equal(vmin, ref["vmin_pu"], equal_nan=True)
     assert got[0][4] == 0 and got[0][5] == got[1][4] and got[1][5] == len(cases)
+
+
+def test_qlimit_event_log_matches_oracle_push_order():
+    """net.qLimitLog (src/limits.jl:75-84): one (iteration, bus, side) entry per PV->PQ switch, in the reference's push
+    order; the device appends them to a compacted list, the host restores (scenario, iteration, bus) order."""
+    g = G.tiled_grid(rows=10, cols=10, augment=True, pv_every=3, pv_q_mvar=8.0)
+    eng, a, vm, va = _warm_engine(g)
+    cases = O.generate_n1_branches(g)[:60]
+    raw = eng.solve_outages(cases, want_lists=True)
+    eng.close()
+    ev = raw["qlimit_events"]
+    assert raw["qlimit_event_total"] == len(ev) == int(raw["n_switch_events"].sum()) > 0
+    per = [[] for _ in cases]
+    for sc, it, bus, side in ev:
+        per[sc].append((int(it), int(bus), "max" if side > 0 else "min"))
+    for i, c in enumerate(cases):
+        r = O.runpf(g, vm, va, c)
+        assert per[i] == [(it, b, s) for it, b, s in r.log], (i, c)
