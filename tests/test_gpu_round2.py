@@ -370,14 +370,15 @@ def test_multi_engine_two_gpus_matches_single_gpu():
     g = G.tiled_grid(rows=12, cols=12, augment=True, pv_every=4, pv_q_mvar=24.0, rating_mva=4.0)
     cases = O.generate_n1_branches(g) + [[3, 40], [10 ** 6], [7, 8]]
     eng, a, vm, va = _warm_engine(g, vm_min_pu=0.995, vm_max_pu=1.015)
-    one = eng.solve_outages(cases, want_lists=True, want_flows=True)
+    one = eng.solve_outages(cases, want_lists=True, want_flows=True, list_capacity=400_000)
     eng.close()
     me = api.MultiEngine(a, 2, vm_min_pu=0.995, vm_max_pu=1.015)
-    two = me.solve_outages(cases, want_lists=True, want_flows=True)
+    two = me.solve_outages(cases, want_lists=True, want_flows=True, list_capacity=400_000)
     st0, st1 = me.stats(0), me.stats(1)
     me.close()
+    assert one["lists_complete"] and two["lists_complete"]
     for k in ("converged", "status", "iterations", "n_switch_events", "island_count", "V", "bus_type_final", "flows",
-              "n_voltage_violations", "n_overloaded", "violations", "overloads"):
+              "n_voltage_violations", "n_overloaded", "violations", "overloads", "qlimit_events"):
         assert np.array_equal(one[k], two[k]), k
     for k in ("final_mismatch", "vmin_pu", "vmax_pu", "max_loading_pct"):
         assert np.array_equal(one[k], two[k], equal_nan=True), k
@@ -385,11 +386,10 @@ def test_multi_engine_two_gpus_matches_single_gpu():
 
 
 def _rank_worker(rank, world, uid_q, out_q, cases):
-    os.environ["CUDA_VISIBLE_DEVICES"] = str(rank)
     g = G.tiled_grid(rows=12, cols=12, augment=True, pv_every=4, pv_q_mvar=24.0)
     vm, va, flat, base = O.solve_base(g)
     a = M.build_arrays(g, vm=vm, va_deg=va)
-    eng = api.Engine(a)
+    eng = api.Engine(a, device=rank)          # one process per GPU: rank r owns device r
     if rank == 0:
         uid = eng.comm_unique_id()
         for _ in range(world - 1):
