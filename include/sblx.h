@@ -182,6 +182,8 @@ typedef struct sblx_stats {
   int64_t n_ranks;               /* ranks (GPUs) that shared the last sharded solve, 1 otherwise */
   int64_t shard_lo, shard_hi;    /* this rank's contiguous scenario range of the last sharded solve */
   double allgather_ms;           /* device time of the one ncclAllGather of the last sharded solve */
+  int64_t refine_passes;         /* iterative-refinement passes (second factor + solve on the residual) run for steps whose
+                                    factorisation met a tiny pivot and whose residual exceeded 1e-6 |F| */
 } sblx_stats;
 
 int sblx_version(void);

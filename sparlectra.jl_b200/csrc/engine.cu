@@ -441,7 +441,10 @@ struct sblx_handle {
   DevBuf<unsigned char> s_type, s_iso, s_evcnt, s_evact;
   DevBuf<short> s_evlast;
   DevBuf<int> s_scen, s_iter, s_state, s_changed, s_nev, s_singular, s_numerical, s_reason, s_viol, s_maxsw, s_rated, s_out_cnt, s_out_br;
-  DevBuf<int> s_nvv, s_nov, s_tiny, s_tinyit;
+  DevBuf<int> s_nvv, s_nov, s_tiny, s_tinyit, s_refine, s_nrefine, l_refine;
+  DevBuf<double> s_fnorm;
+  DevBuf<double2> s_xsave;
+  const Lists* Lover = nullptr;   // list override of the factor / solve launches (refinement pass)
   DevBuf<unsigned long long> s_mis, s_mis2, s_pvres, s_vminb, s_vmaxb, s_loadb;
   DevBuf<int> l_active, l_fresh, l_step, l_fin, l_counts;
   Slots A{};
@@ -744,6 +747,7 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   h->s_singular.alloc(W); h->s_numerical.alloc(W); h->s_reason.alloc(W); h->s_viol.alloc(W); h->s_maxsw.alloc(W);
   h->s_rated.alloc(W); h->s_out_cnt.alloc(W); h->s_out_br.alloc((size_t)W * MAXOUT); h->s_fm.alloc(W);
   h->s_nvv.alloc(W); h->s_nov.alloc(W); h->s_tiny.alloc(W); h->s_tinyit.alloc(W);
+  h->s_refine.alloc(W); h->s_nrefine.alloc(W); h->l_refine.alloc(W); h->s_fnorm.alloc(W); h->s_xsave.alloc(m * W);
   h->s_mis.alloc(W); h->s_mis2.alloc(W); h->s_pvres.alloc(W); h->s_vminb.alloc(W); h->s_vmaxb.alloc(W); h->s_loadb.alloc(W);
   h->l_active.alloc(W); h->l_fresh.alloc(W); h->l_step.alloc(W); h->l_fin.alloc(W); h->l_counts.alloc(8);
   h->W = (int)W;
@@ -759,8 +763,10 @@ static void ensure_slots(sblx_handle* h, int64_t want) {
   A.pvres_bits = h->s_pvres.p; A.vmin_bits = h->s_vminb.p; A.vmax_bits = h->s_vmaxb.p; A.load_bits = h->s_loadb.p;
   A.viol = h->s_viol.p; A.maxsw = h->s_maxsw.p; A.rated = h->s_rated.p; A.out_cnt = h->s_out_cnt.p; A.out_br = h->s_out_br.p;
   A.nvv = h->s_nvv.p; A.nov = h->s_nov.p; A.tiny = h->s_tiny.p; A.tinyit = h->s_tinyit.p;
+  A.refine = h->s_refine.p; A.nrefine = h->s_nrefine.p; A.fnorm = h->s_fnorm.p; A.xsave = h->s_xsave.p;
   Lists& L = h->L;
   L.active = h->l_active.p; L.fresh = h->l_fresh.p; L.step = h->l_step.p; L.fin = h->l_fin.p; L.counts = h->l_counts.p;
+  L.refine = h->l_refine.p;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1129,16 +1135,16 @@ static void launch_front(sblx_handle* h, const LaunchGroup& g, int nstep) {
       g.pf_delta = std::max(1, (int)(h->pf_mult * h->sm_count * std::max(occ, 1)));
     }
   }
-  k_front<NT, G, WIDE><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off, stride, g.pf_delta);
+  k_front<NT, G, WIDE><<<grid, NT, (size_t)stride * 16 * NG, h->stream>>>(h->M, h->A, h->Lover ? *h->Lover : h->L, h->d_panels_lv.p + g.off, stride, g.pf_delta);
 }
 template <int NT>
 static void launch_solve(sblx_handle* h, const LaunchGroup& g, int nstep) {
   dim3 grid(nstep, g.cnt);
-  k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off);
+  k_backsolve<NT><<<grid, NT, g.smem, h->stream>>>(h->M, h->A, h->Lover ? *h->Lover : h->L, h->d_panels_lv.p + g.off);
 }
 static void launch_solve_group(sblx_handle* h, const LaunchGroup& g, int nstep) {
   if (g.lanes == 8) {
-    k_backsolve_small<<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off);
+    k_backsolve_small<<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->Lover ? *h->Lover : h->L, h->d_panels_lv.p + g.off);
     return;
   }
   switch (g.nt) {
@@ -1157,7 +1163,7 @@ static void launch_factor(sblx_handle* h, int nstep) {
       for (const LaunchGroup& g : h->front_groups[l]) {
         switch (g.nt) {
           case 32:
-            if (g.reg) k_front_reg<8, 8><<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->L, h->d_panels_lv.p + g.off);
+            if (g.reg) k_front_reg<8, 8><<<dim3((nstep + 3) / 4, g.cnt), 32, 0, h->stream>>>(h->M, h->A, h->Lover ? *h->Lover : h->L, h->d_panels_lv.p + g.off);
             else if (g.lanes == 4) launch_front<32, 4>(h, g, nstep);
             else if (g.lanes == 8) launch_front<32, 8>(h, g, nstep);
             else if (g.lanes == 16) launch_front<32, 16>(h, g, nstep);
@@ -1206,6 +1212,7 @@ static void run_staged(sblx_handle* h) {
   sblx_stats& st = h->stats;
   // per-run counters (stage-time fields host_prep_ms / h2d_* are kept)
   st.launches = st.factor_launches = st.ticks = st.scenario_iterations = st.mismatch_evaluations = st.scenarios_solved = 0;
+  st.refine_passes = 0;
   st.total_ms = st.factor_ms = st.solve_ms = st.mismatch_ms = st.jacobian_ms = st.other_ms = 0.0;
   // reset slots
   CK(cudaMemsetAsync(h->s_state.p, 0, W * sizeof(int), s));
@@ -1216,7 +1223,7 @@ static void run_staged(sblx_handle* h) {
   int64_t running = 0, qhead = 0;
   const int64_t nq = h->nq;
   double t_mis = 0, t_jac = 0, t_fac = 0, t_sol = 0, t_oth = 0;
-  bool have_prev = false;
+  bool have_prev = false, tiny_mode = (h->M.pf_mode & 2048) != 0;   // test hook: refinement armed from the first tick
   // SBLX_PROFILE_TICK=k brackets tick k (1-based) of this run with cudaProfilerStart/Stop (ncu --profile-from-start off)
   const char* ptick_env = getenv("SBLX_PROFILE_TICK");
   const long ptick = (ptick_env && nq > 1) ? atol(ptick_env) : 0;
@@ -1261,6 +1268,7 @@ static void run_staged(sblx_handle* h) {
       t_mis += a;
     }
     const int nactive = h->pinned_counts[0], nstep = h->pinned_counts[2], nfin = h->pinned_counts[3];
+    if (h->pinned_counts[7] > 0) tiny_mode = true;
     qhead = h->pinned_counts[4];
     running += assign;
     st.ticks++;
@@ -1287,6 +1295,28 @@ static void run_staged(sblx_handle* h) {
       if (h->M.pivot_tol > 0.0) {
         k_tiny_guard<<<nstep, 256, 0, s>>>(h->M, h->A, h->L);
         st.launches++;
+        if (tiny_mode && h->opt.factor_mode != 1) {
+          // a tiny pivot has been met in this run: from now on the refine list is read back right after the guard (one
+          // extra round trip per tick) and flagged steps are repaired before they are applied
+          CK(cudaMemcpyAsync(h->pinned_counts, h->l_counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+          CK(cudaStreamSynchronize(s));
+          const int nref = h->pinned_counts[6];
+          if (nref > 0) {
+            // ONE refinement pass: the factor / solve launches run over the refine list (counts[2] of the override
+            // aliases counts[6]); a step that is still bad afterwards is declared singular
+            Lists Lr = h->L;
+            Lr.step = h->L.refine;
+            Lr.counts = h->L.counts + 4;
+            k_refine_prep<<<nref, 256, 0, s>>>(h->M, h->A, h->L);
+            h->Lover = &Lr;
+            launch_factor(h, nref);
+            for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
+              for (const LaunchGroup& g : h->solve_groups[l]) launch_solve_group(h, g, nref);
+            h->Lover = nullptr;
+            k_refine_post<<<nref, 256, 0, s>>>(h->M, h->A, h->L, 1);
+            st.refine_passes += nref;
+          }
+        }
       }
       dim3 g((m + 7) / 8, (nstep + 31) / 32);
       k_update<<<g, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);

@@ -87,13 +87,15 @@ struct Slots {
   int* scen; int* iter; int* state; int* changed; int* nev; int* singular; int* numerical; int* reason;
   unsigned long long* mis_bits; unsigned long long* mis2_bits; double* fm;
   unsigned long long* pvres_bits; unsigned long long* vmin_bits; unsigned long long* vmax_bits; unsigned long long* load_bits;
-  int* viol; int* maxsw; int* rated; int* nvv; int* nov; int* tiny; int* tinyit;   // nvv / nov: voltage-band violations / overloaded branches; tiny: near-singular pivot blocks
+  int* viol; int* maxsw; int* rated; int* nvv; int* nov; int* tiny; int* tinyit;
+  int* refine; int* nrefine; double* fnorm; double2* xsave;   // iterative refinement of steps whose factorisation met a tiny pivot   // nvv / nov: voltage-band violations / overloaded branches; tiny: near-singular pivot blocks
   int* out_cnt; int* out_br;   // [W][MAXOUT]
 };
 
 struct Lists {
   int* active; int* fresh; int* step; int* fin;
-  int* counts;   // [0] nActive [1] nFresh [2] nStep [3] nFin [4] queue head [5] nDrain
+  int* counts;   // [0] nActive [1] nFresh [2] nStep [3] nFin [4] queue head [5] nDrain [6] steps to refine in this tick [7] ... so far in this run
+  int* refine;   // slots whose step needs iterative refinement (filled by k_tiny_guard)
 };
 
 struct Batch {
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(1024) k_assign(DevModel M, Slots A, Lists L, B
       A.mis2_bits[slot] = 0ull;
       A.changed[slot] = 0;
       A.tinyit[slot] = 0;
+      A.refine[slot] = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) s_nact = na + s_total;
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(1024) k_assign(DevModel M, Slots A, Lists L, B
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    L.counts[6] = 0;
     L.counts[0] = s_nact;
     L.counts[1] = s_nfresh;
     L.counts[4] = s_qhead;
@@ -305,6 +309,7 @@ __global__ void __launch_bounds__(256) k_init(DevModel M, Slots A, Lists L, Batc
     A.reason[slot] = 1;
     A.fm[slot] = 0.0;
     A.tiny[slot] = 0;
+    A.nrefine[slot] = 0;
     int cnt = 0;
     if (Bt.out_ptr) {
       int b = Bt.out_ptr[scen], e = Bt.out_ptr[scen + 1];
@@ -1709,39 +1714,34 @@ __global__ void __launch_bounds__(32) k_backsolve_small(DevModel M, Slots A, Lis
 }
 
 // Safety net of the static-pivoting LU (the reference's UMFPACK pivots across rows and falls back to QR / SVD,
-// solver_core.jl:60-82): a factorisation that met a tiny pivot block re-checks its own solve.  One CTA per stepping
-// scenario, immediately out unless the scenario was flagged in THIS iteration: r = (-F) - J dx with the stored
-// Jacobian blocks (scratch: the y vector, dead after the back substitution); a step whose residual exceeds
-// 1e-6 |F|_inf is not applied - the scenario ends as singular_newton_step instead of silently taking a bad step.
-__global__ void __launch_bounds__(256) k_tiny_guard(DevModel M, Slots A, Lists L) {
-  __shared__ double red[2][256];
-  if ((int)blockIdx.x >= L.counts[2]) return;
-  const int slot = L.step[blockIdx.x];
-  if (!A.tinyit[slot] || A.singular[slot]) return;
-  double2* r = A.yv + (size_t)slot * M.m;
-  const double2* rhs = A.rhs + (size_t)slot * M.m;
-  const double2* x = A.xv + (size_t)slot * M.m;
+// solver_core.jl:60-82).  A factorisation that met a tiny pivot block re-checks its own solve: r = b - J x with the stored
+// Jacobian blocks.  If |r|_inf > 1e-6 |b|_inf the step is NOT applied as it is: the slot goes to the refine list and the
+// host runs iterative refinement on it (second factor + solve pass on the residual, x += dx, at most two passes); a step
+// that cannot be repaired ends the scenario as singular_newton_step instead of silently taking a bad step.
+// r is left in the y vector (dead after the back substitution).  Block-wide; returns (|r|_inf, |b|_inf) to thread 0.
+__device__ __forceinline__ void step_residual(const DevModel& M, const Slots& A, int slot, const double2* b, const double2* x, double2* r,
+                                              double (*red)[256], double& mr_out, double& mb_out) {
   const double* Jv = A.Jv + (size_t)slot * M.nnzB * 4;
-  for (int e = threadIdx.x; e < M.m; e += 256) r[e] = rhs[e];
+  for (int e = threadIdx.x; e < M.m; e += 256) r[e] = b[e];
   __syncthreads();
   for (int k = threadIdx.x; k < M.nnzB; k += 256) {
     const int er = M.elim_of_node[M.jb_row[k]], ec = M.elim_of_node[M.jb_col[k]];
     const double2 xc = x[ec];
-    const double* b = Jv + 4 * (size_t)k;
-    atomicAdd(&r[er].x, -(b[0] * xc.x + b[1] * xc.y));
-    atomicAdd(&r[er].y, -(b[2] * xc.x + b[3] * xc.y));
+    const double* q = Jv + 4 * (size_t)k;
+    atomicAdd(&r[er].x, -(q[0] * xc.x + q[1] * xc.y));
+    atomicAdd(&r[er].y, -(q[2] * xc.x + q[3] * xc.y));
   }
   __syncthreads();
-  double mr = 0.0, mf = 0.0;
+  double mr = 0.0, mb = 0.0;
   bool bad = false;
   for (int e = threadIdx.x; e < M.m; e += 256) {
-    const double2 a = r[e], f = rhs[e];
+    const double2 a = r[e], f = b[e];
     bad |= !(isfinite(a.x) && isfinite(a.y));
     mr = fmax(mr, fmax(fabs(a.x), fabs(a.y)));
-    mf = fmax(mf, fmax(fabs(f.x), fabs(f.y)));
+    mb = fmax(mb, fmax(fabs(f.x), fabs(f.y)));
   }
   red[0][threadIdx.x] = bad ? INFINITY : mr;
-  red[1][threadIdx.x] = mf;
+  red[1][threadIdx.x] = mb;
   __syncthreads();
   for (int s2 = 128; s2 > 0; s2 >>= 1) {
     if ((int)threadIdx.x < s2) {
@@ -1750,7 +1750,59 @@ __global__ void __launch_bounds__(256) k_tiny_guard(DevModel M, Slots A, Lists L
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0 && !(red[0][0] <= 1e-6 * fmax(red[1][0], 1e-300))) A.singular[slot] = 1;
+  mr_out = red[0][0];
+  mb_out = red[1][0];
+  __syncthreads();
+}
+
+// grid nStep, block 256: immediately out unless the scenario was flagged in THIS iteration
+__global__ void __launch_bounds__(256) k_tiny_guard(DevModel M, Slots A, Lists L) {
+  __shared__ double red[2][256];
+  if ((int)blockIdx.x >= L.counts[2]) return;
+  const int slot = L.step[blockIdx.x];
+  if (!A.tinyit[slot] || A.singular[slot]) return;
+  double mr, mb;
+  step_residual(M, A, slot, A.rhs + (size_t)slot * M.m, A.xv + (size_t)slot * M.m, A.yv + (size_t)slot * M.m, red, mr, mb);
+  if (threadIdx.x == 0) {
+    const bool force = (M.pf_mode & 1024) != 0;              // test hook: refine every flagged step
+    if (force || !(mr <= 1e-6 * fmax(mb, 1e-300))) {
+      A.refine[slot] = 1;
+      A.fnorm[slot] = mb;
+      L.refine[atomicAdd(&L.counts[6], 1)] = slot;
+      atomicAdd(&L.counts[7], 1);
+    }
+  }
+}
+
+// refinement pass, before the second factor + solve: keep x, make the residual the new right-hand side.  grid nRefine
+__global__ void __launch_bounds__(256) k_refine_prep(DevModel M, Slots A, Lists L) {
+  if ((int)blockIdx.x >= L.counts[6]) return;
+  const int slot = L.refine[blockIdx.x];
+  double2* xs = A.xsave + (size_t)slot * M.m;
+  double2* rhs = A.rhs + (size_t)slot * M.m;
+  const double2* x = A.xv + (size_t)slot * M.m;
+  const double2* r = A.yv + (size_t)slot * M.m;
+  for (int e = threadIdx.x; e < M.m; e += 256) { xs[e] = x[e]; rhs[e] = r[e]; }
+}
+
+// after it: x = x_saved + dx, r' = r - J dx; accept when |r'| <= 1e-6 |b|, else keep the slot for another pass
+// (`last` = no pass left: the step is declared singular).  grid nRefine
+__global__ void __launch_bounds__(256) k_refine_post(DevModel M, Slots A, Lists L, int last) {
+  __shared__ double red[2][256];
+  if ((int)blockIdx.x >= L.counts[6]) return;
+  const int slot = L.refine[blockIdx.x];
+  if (!A.refine[slot]) return;
+  if (A.singular[slot]) { if (threadIdx.x == 0) A.refine[slot] = 0; return; }     // the second factorisation hit an exactly singular block
+  double2* x = A.xv + (size_t)slot * M.m;
+  double mr, mb;
+  step_residual(M, A, slot, A.rhs + (size_t)slot * M.m, x, A.yv + (size_t)slot * M.m, red, mr, mb);
+  const double2* xs = A.xsave + (size_t)slot * M.m;
+  for (int e = threadIdx.x; e < M.m; e += 256) x[e] = cadd(x[e], xs[e]);
+  if (threadIdx.x == 0) {
+    A.nrefine[slot] += 1;
+    if (mr <= 1e-6 * fmax(A.fnorm[slot], 1e-300)) A.refine[slot] = 0;
+    else if (last) { A.refine[slot] = 0; A.singular[slot] = 1; }
+  }
 }
 
 // V += damp * dx (slack untouched).  grid (ceil(m/8), ceil(nStep/32)), block (32, 8)
@@ -1760,7 +1812,7 @@ __global__ void __launch_bounds__(256) k_update(DevModel M, Slots A, Lists L) {
   const int node = blockIdx.x * 8 + threadIdx.y;
   if (li >= ns || node >= M.m) return;
   const int slot = L.step[li];
-  if (A.singular[slot]) return;                      // the reference breaks before applying the step
+  if (A.singular[slot] || A.refine[slot]) return;    // the reference breaks before applying the step; a step waiting for refinement is withheld
   const int bus = M.bus_of_node[node];
   const double2 dx = A.xv[(size_t)slot * M.m + M.elim_of_node[node]];
   const size_t k = (size_t)bus * M.W + slot;
@@ -1775,6 +1827,7 @@ __global__ void k_poststep(DevModel M, Slots A, Lists L) {
   if (li >= L.counts[2]) return;
   const int slot = L.step[li];
   if (A.singular[slot]) { A.state[slot] = ST_DRAIN; A.numerical[slot] = 0; A.reason[slot] = 3; }
+  else if (A.refine[slot]) { A.iter[slot] -= 1; }    // not refined in this tick (the host learns of it one tick late): the iteration is repeated
   else if (A.iter[slot] >= M.max_iter) { A.state[slot] = ST_DRAIN; A.numerical[slot] = 0; A.reason[slot] = 1; }
 }
 

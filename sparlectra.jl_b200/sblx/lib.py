@@ -60,7 +60,7 @@ class Stats(C.Structure):
         ("scenario_iterations", C.c_int64), ("mismatch_evaluations", C.c_int64), ("scenarios_solved", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("tiny_pivots", C.c_int64), ("n_ranks", C.c_int64), ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
-        ("allgather_ms", C.c_double),
+        ("allgather_ms", C.c_double), ("refine_passes", C.c_int64),
     ]
 
 

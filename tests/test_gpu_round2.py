@@ -442,3 +442,31 @@ def test_qlimit_event_log_matches_oracle_push_order():
     for i, c in enumerate(cases):
         r = O.runpf(g, vm, va, c)
         assert per[i] == [(it, b, s) for it, b, s in r.log], (i, c)
+
+
+@pytest.mark.parametrize("prearmed", [True, False])
+def test_iterative_refinement_path_keeps_parity(prearmed):
+    """The safety net of the static-pivoting LU: a step whose factorisation met a tiny pivot and whose residual is bad gets
+    one pass of iterative refinement (second factor + solve on the residual).  Forced here on healthy systems (every pivot
+    flagged, every flagged step treated as bad): the refined steps must leave converged flag, iteration count, active set
+    and voltages unchanged.  `prearmed` = False also exercises the first offender's path (step withheld, iteration
+    repeated one tick later with refinement on)."""
+    g = G.tiled_grid(rows=12, cols=12, augment=True, pv_every=4, pv_q_mvar=24.0)
+    vm, va, flat, base = O.solve_base(g)
+    a = M.build_arrays(g, vm=vm, va_deg=va)
+    cases = O.generate_n1_branches(g)[:48]
+    eng = api.Engine(a, pivot_tol_rel=1e3)
+    ref = eng.solve_outages(cases)
+    assert eng.stats()["refine_passes"] == 0 and ref["n_tiny_pivots"].min() > 0
+    eng.lib.sblx_debug_set_pf_mode(eng.h, 1024 | (2048 if prearmed else 0))
+    raw = eng.solve_outages(cases)
+    st = eng.stats()
+    eng.close()
+    assert st["refine_passes"] >= int(raw["iterations"].sum()) - 2 * len(cases)
+    oracle = O.run_contingencies(g, cases)
+    for i, o in enumerate(oracle):
+        assert bool(raw["converged"][i]) == o.converged and int(raw["iterations"][i]) == o.iterations, i
+        if o.converged:
+            assert np.max(np.abs(raw["V"][i] - o.V)) <= VTOL
+            assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8))
+    assert np.array_equal(raw["iterations"], ref["iterations"]) and np.max(np.abs(raw["V"] - ref["V"])) <= 1e-10
