@@ -214,8 +214,10 @@ int sblx_get_stats(const sblx_handle* h, sblx_stats* stats);
 
 /* N-k outages: scenario s takes branches outage_branch[outage_ptr[s] .. outage_ptr[s+1]) out of
  * service (an empty range is the intact grid).  outage_ptr is 0-based regardless of index_base;
- * branch ids follow index_base.  At most 8 branches per scenario; a scenario with more, or with an id that is
- * not a branch of the model, is reported with status SBLX_ST_BAD_BRANCH (never an error return).  Outages that
+ * branch ids follow index_base.  Duplicate ids within a scenario count once (a branch can only be removed once).  At
+ * most 8 distinct branches per scenario; a scenario with more, or with an id that is not a branch of the model, is
+ * reported with status SBLX_ST_BAD_BRANCH (never an error return); outage_ptr must start at 0 and be non-decreasing
+ * (SBLX_E_ARG otherwise).  Outages that
  * isolate buses or split the grid are handled like the reference does (identity rows; island-wise solves with
  * reference promotion; SBLX_ST_ISLANDED_NO_REF when an island with branches has no slack or PV bus). */
 int sblx_solve_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, const int32_t* outage_branch,
