@@ -352,6 +352,26 @@ def main():
                    "call": "runContingenciesBatched(grid, generateN1Branches(grid)): engine creation + symbolic analysis + base solve + "
                            "one batched solve with device-side lists + ContingencyResult objects"}
 
+    # ---- BASELINE configs 1 / 2 as latencies (rank 0, N = 1): wall clock of one sblx_solve_outages call on tiny batches
+    small = None
+    if rank == 0 and world == 1 and args.config == "n1_10k" and not args.scenarios:
+        from sblx import grid as G
+        small = {}
+        for nm, gs in (("ieee14_full_n1", G.case14()), ("ladder118_full_n1", G.warmup_case118())):
+            es = api.Engine(M.build_arrays(gs), device=local_rank)
+            Vs, *_ = es.solve_one(None)
+            es.set_v0(M.build_arrays(gs, vm=np.abs(Vs), va_deg=np.degrees(np.angle(Vs))).v0)
+            cs = [[k] for k in range(gs.nbranch)]
+            es.solve_outages(cs)
+            ts = []
+            for _ in range(5):
+                w0 = time.perf_counter()
+                rs = es.solve_outages(cs)
+                ts.append(time.perf_counter() - w0)
+            sst = es.stats()
+            small[nm] = {"scenarios": len(cs), "ms": 1e3 * min(ts), "converged": int(rs["converged"].sum()), "ticks": sst["ticks"], "launches": sst["launches"]}
+            es.close()
+
     # ---- CPU baseline + parity gate (rank 0, N = 1)
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not sweep:
@@ -430,6 +450,8 @@ def main():
         }
         if api_e2e:
             line["e2e_api"] = api_e2e
+        if small:
+            line["small_batch_latency"] = small
         if cpu:
             line["cpu_baseline"] = cpu
         if parity:

@@ -480,6 +480,8 @@ struct sblx_handle {
   HostResults hostres;       // host-decided scenarios (islanded / bad branch), status < 0 = solved on device
   int64_t nq = 0;
   int* pinned_counts = nullptr;
+  void* pinned_stage[2] = {nullptr, nullptr};   // staging buffers of h2d_staged
+  cudaEvent_t stage_ev[2] = {};
   sblx_stats stats{};
   cudaEvent_t ev[8] = {};
 
@@ -489,6 +491,10 @@ struct sblx_handle {
       for (auto& e : ev)
         if (e) cudaEventDestroy(e);
       if (pinned_counts) cudaFreeHost(pinned_counts);
+      for (int k = 0; k < 2; ++k) {
+        if (pinned_stage[k]) cudaFreeHost(pinned_stage[k]);
+        if (stage_ev[k]) cudaEventDestroy(stage_ev[k]);
+      }
       if (stream) cudaStreamDestroy(stream);
       if (comm && comm_owned) sblx::nccl_destroy(comm);
     }
@@ -969,6 +975,38 @@ static void set_batch(sblx_handle* h) {
   Bt.r_fm = h->r_fm.p; Bt.r_vmin = h->r_vmin.p; Bt.r_vmax = h->r_vmax.p; Bt.r_load = h->r_load.p;
   Bt.r_V = h->r_V.p; Bt.r_types = h->r_types.p;
   h->A.qload_s = h->sweep_q ? h->s_qload.p : nullptr;
+}
+
+// Host -> device copy of a large caller array through two pinned staging buffers: the caller's memory is pageable (Julia /
+// numpy arrays), a direct cudaMemcpy from it is staged by the driver in small pieces; here a host thread's memcpy into
+// pinned chunk k + 1 overlaps the DMA of chunk k.
+static void h2d_staged(sblx_handle* h, void* dst, const void* src, size_t bytes) {
+  const size_t CH = 32u << 20;
+  if (bytes <= CH) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return;
+  }
+  if (!h->pinned_stage[0]) {
+    CK(cudaMallocHost(&h->pinned_stage[0], CH));
+    CK(cudaMallocHost(&h->pinned_stage[1], CH));
+    CK(cudaEventCreateWithFlags(&h->stage_ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->stage_ev[1], cudaEventDisableTiming));
+  }
+  size_t off = 0;
+  int k = 0;
+  bool used[2] = {false, false};
+  while (off < bytes) {
+    const size_t nb = std::min(CH, bytes - off);
+    if (used[k]) CK(cudaEventSynchronize(h->stage_ev[k]));          // the DMA that last read this buffer is done
+    memcpy(h->pinned_stage[k], (const char*)src + off, nb);
+    CK(cudaMemcpyAsync((char*)dst + off, h->pinned_stage[k], nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->stage_ev[k], h->stream));
+    used[k] = true;
+    off += nb;
+    k ^= 1;
+  }
+  CK(cudaStreamSynchronize(h->stream));
 }
 
 static void stage_outages(sblx_handle* h, int64_t B, const int32_t* optr, const int32_t* obr, const Want& want) {
@@ -2087,15 +2125,14 @@ int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const
   const size_t cnt = (size_t)B * h->H.n;
   const double t0 = now_ms();
   h->b_S.alloc(cnt);
-  CK(cudaMemcpyAsync(h->b_S.p, s_spec, cnt * 16, cudaMemcpyHostToDevice, h->stream));
+  h2d_staged(h, h->b_S.p, s_spec, cnt * 16);
   h->stats.h2d_bytes += (int64_t)cnt * 16;
   if (qload_pu) {
     h->b_ql.alloc(cnt);
-    CK(cudaMemcpyAsync(h->b_ql.p, qload_pu, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    h2d_staged(h, h->b_ql.p, qload_pu, cnt * 8);
     h->stats.h2d_bytes += (int64_t)cnt * 8;
     h->sweep_q = true;
   }
-  CK(cudaStreamSynchronize(h->stream));
   h->stats.h2d_ms += now_ms() - t0;
   set_batch(h);
   run_staged(h);

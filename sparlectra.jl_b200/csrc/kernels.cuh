@@ -132,6 +132,11 @@ __device__ __forceinline__ void ldg_blk(const double2* p, double2& r0, double2& 
   asm("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r0.x), "=d"(r0.y), "=d"(r1.x), "=d"(r1.y) : "l"(__cvta_generic_to_global(p)));
 #endif
 }
+// same load, pinned in program order (volatile): for requests that must be ISSUED before a long arithmetic loop whose
+// result they are only added to afterwards - ptxas otherwise sinks the load to its first use
+__device__ __forceinline__ void ldg_blk_early(const double2* p, double2& r0, double2& r1) {
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r0.x), "=d"(r0.y), "=d"(r1.x), "=d"(r1.y) : "l"(__cvta_generic_to_global(p)) : "memory");
+}
 __device__ __forceinline__ void stg_blk(double2* p, double2 r0, double2 r1) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "d"(r0.x), "d"(r0.y), "d"(r1.x), "d"(r1.y) : "memory");
 }
@@ -1024,6 +1029,82 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
   double2* Co = reinterpret_cast<double2*>(Cs + P.c_off * 4);
   SBLX_CHECK(P.c_off >= 0 && P.c_off + (long long)h * h + (h + 1) / 2 <= M.c_blocks);
   // ---- Schur complement straight to HBM: C = gather(children) - L * U'
+#ifdef SBLX_SCHUR_EARLY
+  if (NT >= 128) {
+    // Variant: warp-level work items of 4 structure rows x 32 structure columns, and the FIRST child's blocks of the item
+    // are requested BEFORE the FMA loop (into registers that nothing touches until the loop is done), so that their HBM
+    // round trip overlaps the arithmetic instead of following it.  16 accumulators + 16 prefetch registers (double2 x 8
+    // each) instead of 32 + 32 at the gather; per pivot 2 U' loads (consecutive words) + 8 L broadcasts for 32 DFMA.
+    const int lane = tid & 31, warp = tid >> 5, nwarp = NT / 32;
+    const int ncg = (h + 31) >> 5, nrg = (h + 3) >> 2;
+    const int nch = ABL(16) ? 0 : (int)P.nchild;
+    for (int item = warp; item < nrg * ncg; item += nwarp) {
+      const int rg = item / ncg, cg = item - rg * ncg;
+      const int a0 = rg * 4;
+      const int bA = cg * 32 + lane;
+      const bool vA = bA < h;
+      const int cA = vA ? bA : h - 1;
+      int ar[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ar[i] = min(a0 + i, h - 1);
+      double2 g[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { g[i][0] = make_double2(0.0, 0.0); g[i][1] = g[i][0]; }
+      if (nch > 0) {
+        const ChildDev Cd = M.childdev[P.child_ptr];
+        const int hc = Cd.hc;
+        const int* inv = M.inv + Cd.inv_off;
+        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
+        const int ibA = vA ? inv[bA] : -1;
+        SBLX_CHECK(ibA < hc && Cd.c_off >= 0 && Cd.c_off + (long long)hc * hc <= M.c_blocks);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ia = (a0 + i < h) ? inv[a0 + i] : -1;
+          SBLX_CHECK(ia < hc);
+          if (ia >= 0 && ibA >= 0) ldg_blk_early(Cm + 2 * ((size_t)ia * hc + ibA), g[i][0], g[i][1]);
+        }
+      }
+      double2 acc[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[i][0] = make_double2(0.0, 0.0); acc[i][1] = acc[i][0]; }
+      const double2* u0p = T0 + w + cA;
+      const double2* u1p = T1 + w + cA;
+#pragma unroll 4
+      for (int p = 0; p < (ABL(8) ? 0 : w); ++p) {
+        const double2 ua0 = u0p[p * nf], ua1 = u1p[p * nf];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double2 l0 = L0[p * h + ar[i]], l1 = L1[p * h + ar[i]];
+          bmsub(acc[i][0], acc[i][1], l0, l1, ua0, ua1);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[i][0] = cadd(acc[i][0], g[i][0]); acc[i][1] = cadd(acc[i][1], g[i][1]); }
+      for (int ci = 1; ci < nch; ++ci) {
+        const ChildDev Cd = M.childdev[P.child_ptr + ci];
+        const int hc = Cd.hc;
+        const int* inv = M.inv + Cd.inv_off;
+        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
+        const int ibA = vA ? inv[bA] : -1;
+        SBLX_CHECK(ibA < hc && Cd.c_off >= 0 && Cd.c_off + (long long)hc * hc <= M.c_blocks);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ia = (a0 + i < h) ? inv[a0 + i] : -1;
+          g[i][0] = make_double2(0.0, 0.0); g[i][1] = g[i][0];
+          if (ia >= 0 && ibA >= 0) ldg_blk(Cm + 2 * ((size_t)ia * hc + ibA), g[i][0], g[i][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i][0] = cadd(acc[i][0], g[i][0]); acc[i][1] = cadd(acc[i][1], g[i][1]); }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (a0 + i >= h) break;
+        if (ABL(32) && acc[i][0].x != 123.456) continue;
+        if (vA) stg_blk(Co + 2 * ((a0 + i) * h + bA), acc[i][0], acc[i][1]);
+      }
+    }
+  } else
+#endif
   if (NT >= 128) {
     // warp-level work items: 4 structure rows x 64 structure columns; lane l owns columns (cg*64 + l) and
     // (cg*64 + 32 + l): L loads are warp broadcasts, U' loads are consecutive 16 B words (no bank conflicts),
@@ -1107,6 +1188,26 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
 #pragma unroll
         for (int y = 0; y < 2; ++y) { acc[x][y][0] = make_double2(0.0, 0.0); acc[x][y][1] = make_double2(0.0, 0.0); }
       const int a1i = va ? a0 + 1 : a0, b1i = vb ? b0 + 1 : b0;
+#ifdef SBLX_SCHUR_EARLY_SMALL
+      // the first child's four blocks are requested before the FMA loop (see the large-front variant)
+      double2 g[2][2][2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) { g[x][y][0] = make_double2(0.0, 0.0); g[x][y][1] = g[x][y][0]; }
+      if (P.nchild > 0) {
+        const ChildDev Cd = M.childdev[P.child_ptr];
+        const int hc = Cd.hc;
+        const int* inv = M.inv + Cd.inv_off;
+        const double2* Cm = reinterpret_cast<const double2*>(Cs + Cd.c_off * 4);
+        const int ia0 = inv[a0], ia1 = va ? inv[a0 + 1] : -1;
+        const int ib0 = inv[b0], ib1 = vb ? inv[b0 + 1] : -1;
+        if (ia0 >= 0 && ib0 >= 0) ldg_blk_early(Cm + 2 * (ia0 * hc + ib0), g[0][0][0], g[0][0][1]);
+        if (ia0 >= 0 && ib1 >= 0) ldg_blk_early(Cm + 2 * (ia0 * hc + ib1), g[0][1][0], g[0][1][1]);
+        if (ia1 >= 0 && ib0 >= 0) ldg_blk_early(Cm + 2 * (ia1 * hc + ib0), g[1][0][0], g[1][0][1]);
+        if (ia1 >= 0 && ib1 >= 0) ldg_blk_early(Cm + 2 * (ia1 * hc + ib1), g[1][1][0], g[1][1][1]);
+      }
+#endif
       for (int p = 0; p < w; ++p) {
         const double2 la0 = L0[p * h + a0], la1 = L1[p * h + a0];
         const double2 lb0 = L0[p * h + a1i], lb1 = L1[p * h + a1i];
@@ -1117,7 +1218,15 @@ k_front(DevModel M, Slots A, Lists L, const PanelDev* __restrict__ group_panels,
         bmsub(acc[1][0][0], acc[1][0][1], lb0, lb1, ua0, ua1);
         bmsub(acc[1][1][0], acc[1][1][1], lb0, lb1, ub0, ub1);
       }
+#ifdef SBLX_SCHUR_EARLY_SMALL
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) { acc[x][y][0] = cadd(acc[x][y][0], g[x][y][0]); acc[x][y][1] = cadd(acc[x][y][1], g[x][y][1]); }
+      for (int ci = 1; ci < P.nchild; ++ci) {
+#else
       for (int ci = 0; ci < P.nchild; ++ci) {
+#endif
         const ChildDev Cd = M.childdev[P.child_ptr + ci];
         const int hc = Cd.hc;
         const int* inv = M.inv + Cd.inv_off;
