@@ -44,10 +44,13 @@ struct CudaError : std::runtime_error {
 template <class T>
 struct DevBuf {
   T* p = nullptr;
-  size_t n = 0;
+  size_t n = 0, cap = 0;
+  // Grows only: a buffer that is large enough is reused (cudaMalloc / cudaFree cost tens of microseconds each, and a
+  // small batch stages about two dozen of them - more than its whole solve).  release() really frees.
   void alloc(size_t count) {
+    if (count > 0 && count <= cap && p) { n = count; return; }
     release();
-    n = count;
+    n = cap = count;
     if (count) CK(cudaMalloc(&p, count * sizeof(T)));
   }
   void upload(const std::vector<T>& v, cudaStream_t s = 0) {
@@ -57,7 +60,7 @@ struct DevBuf {
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
-    n = 0;
+    n = cap = 0;
   }
   ~DevBuf() { release(); }
   DevBuf() = default;
