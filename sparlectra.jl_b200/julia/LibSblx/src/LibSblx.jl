@@ -80,10 +80,6 @@ multi_last_error(m::Ptr{Cvoid}) = unsafe_string(ccall((:sblx_multi_last_error, l
 check(rc::Integer, h::Ptr{Cvoid} = C_NULL) = rc == 0 ? nothing : throw(SblxError(rc, last_error(h)))
 check_multi(rc::Integer, m::Ptr{Cvoid}) = rc == 0 ? nothing : throw(SblxError(rc, multi_last_error(m)))
 
-const CREATE_ARGS = (Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                     Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ref{Options})
-
 "One engine handle (ndev == 1: sblx_create) or one engine per GPU with an NCCL communicator (sblx_create_multi)."
 mutable struct Handle
   ptr::Ptr{Cvoid}
@@ -116,14 +112,25 @@ function create(n::Int, colptr::Vector{Int64}, rowval::Vector{Int64}, nz::Vector
   opt.struct_size = sizeof(Options)
   href = Ref{Ptr{Cvoid}}(C_NULL)
   p(x) = x === nothing ? Ptr{Float64}(C_NULL) : Ptr{Float64}(pointer(x))
+  # ccall needs literal type tuples and explicit arguments (no splatting), hence the two spelled-out calls
   GC.@preserve colptr rowval nz bt vset s v0 qmin qmax qload from to y11 y12 y21 y22 rating status opt begin
-    tail = (n, pointer(colptr), pointer(rowval), p(nz), slack, pointer(bt), pointer(vset), p(s), p(v0), p(qmin), p(qmax), p(qload),
-            length(from), isempty(from) ? Ptr{Int32}(C_NULL) : pointer(from), isempty(to) ? Ptr{Int32}(C_NULL) : pointer(to),
-            p(y11), p(y12), p(y21), p(y22), p(rating), status === nothing ? Ptr{UInt8}(C_NULL) : pointer(status), opt)
+    pf = isempty(from) ? Ptr{Int32}(C_NULL) : pointer(from)
+    pt = isempty(to) ? Ptr{Int32}(C_NULL) : pointer(to)
+    ps = status === nothing ? Ptr{UInt8}(C_NULL) : pointer(status)
     if n_devices <= 1
-      check(ccall((:sblx_create, libsblx), Cint, (Ref{Ptr{Cvoid}}, CREATE_ARGS...), href, tail...))
+      check(ccall((:sblx_create, libsblx), Cint,
+        (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ref{Options}),
+        href, n, pointer(colptr), pointer(rowval), p(nz), slack, pointer(bt), pointer(vset), p(s), p(v0), p(qmin), p(qmax), p(qload),
+        length(from), pf, pt, p(y11), p(y12), p(y21), p(y22), p(rating), ps, opt))
     else
-      check(ccall((:sblx_create_multi, libsblx), Cint, (Ref{Ptr{Cvoid}}, Int32, Ptr{Int32}, CREATE_ARGS...), href, Int32(n_devices), C_NULL, tail...))
+      check(ccall((:sblx_create_multi, libsblx), Cint,
+        (Ref{Ptr{Cvoid}}, Int32, Ptr{Int32}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ref{Options}),
+        href, Int32(n_devices), Ptr{Int32}(C_NULL), n, pointer(colptr), pointer(rowval), p(nz), slack, pointer(bt), pointer(vset), p(s), p(v0),
+        p(qmin), p(qmax), p(qload), length(from), pf, pt, p(y11), p(y12), p(y21), p(y22), p(rating), ps, opt))
     end
   end
   return Handle(href[], n_devices > 1, n, length(from))
