@@ -224,7 +224,8 @@ int sblx_solve_outages(sblx_handle* h, int64_t B, const int32_t* outage_ptr, con
                        sblx_results* res);
 
 /* Injection sweep: scenario s uses s_spec[s*n .. (s+1)*n) (interleaved complex) and, when given,
- * qload_pu[s*n ..] instead of the model's vectors. */
+ * qload_pu[s*n ..] instead of the model's vectors.  The matrices are streamed through the device in chunks of
+ * scenarios (pinned staging, about 4 GB per chunk): B x n is never resident at once. */
 int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const double* qload_pu,
                           sblx_results* res);
 

@@ -2119,27 +2119,74 @@ int sblx_multi_solve_outages(sblx_multi* m, int64_t B, const int32_t* outage_ptr
   return SBLX_OK;
 }
 
-int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const double* qload_pu, sblx_results* res) {
-  if (!h || !res || B < 0) return SBLX_E_ARG;
-  API_BEGIN(h)
-  if (B == 0) return SBLX_OK;
-  if (!s_spec) throw std::invalid_argument("sblx_solve_injections: s_spec is NULL");
-  stage_outages(h, B, nullptr, nullptr, want_from(res));
-  const size_t cnt = (size_t)B * h->H.n;
+// One chunk of an explicit injection sweep: scenarios [b0, b0 + nb) of the caller's matrices, results written at row b0.
+static void solve_injections_chunk(sblx_handle* h, int64_t b0, int64_t nb, const double* s_spec, const double* qload_pu, sblx_results* res) {
+  const int n = h->H.n;
+  stage_outages(h, nb, nullptr, nullptr, want_from(res));
+  const size_t cnt = (size_t)nb * n;
   const double t0 = now_ms();
   h->b_S.alloc(cnt);
-  h2d_staged(h, h->b_S.p, s_spec, cnt * 16);
+  h2d_staged(h, h->b_S.p, s_spec + (size_t)b0 * n * 2, cnt * 16);
   h->stats.h2d_bytes += (int64_t)cnt * 16;
   if (qload_pu) {
     h->b_ql.alloc(cnt);
-    h2d_staged(h, h->b_ql.p, qload_pu, cnt * 8);
+    h2d_staged(h, h->b_ql.p, qload_pu + (size_t)b0 * n, cnt * 8);
     h->stats.h2d_bytes += (int64_t)cnt * 8;
     h->sweep_q = true;
   }
   h->stats.h2d_ms += now_ms() - t0;
   set_batch(h);
   run_staged(h);
-  fetch_results(h, res);
+  fetch_results(h, res, b0);
+}
+
+int sblx_solve_injections(sblx_handle* h, int64_t B, const double* s_spec, const double* qload_pu, sblx_results* res) {
+  if (!h || !res || B < 0) return SBLX_E_ARG;
+  API_BEGIN(h)
+  if (B == 0) return SBLX_OK;
+  if (!s_spec) throw std::invalid_argument("sblx_solve_injections: s_spec is NULL");
+  // The per-scenario injection matrices are streamed through the device in chunks of scenarios, so a large sweep never
+  // needs B x n resident (16 + 8 bytes per bus and scenario: 2.4 GB per 10 000 scenarios of a 10k-bus grid).
+  double budget_gb = 4.0;
+  if (const char* e = getenv("SBLX_SWEEP_CHUNK_GB")) budget_gb = std::max(1e-6, atof(e));
+  const int64_t per = (int64_t)h->H.n * (qload_pu ? 24 : 16);
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(budget_gb * 1e9) / per));
+  if (chunk >= B) {
+    solve_injections_chunk(h, 0, B, s_spec, qload_pu, res);
+  } else {
+    // lists: every chunk appends behind the previous one; counts and the run statistics accumulate
+    sblx_results rc = *res;
+    int64_t vtot = 0, otot = 0, qtot = 0, vw = 0, ow = 0, qw = 0, cv = 0, co = 0, cq = 0;
+    sblx_stats acc{};
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+      const int64_t nb = std::min(chunk, B - b0);
+      if (res->viol_scenario) { rc.viol_scenario = res->viol_scenario + vw; rc.viol_bus = res->viol_bus + vw; rc.viol_capacity = res->viol_capacity - vw; rc.viol_count = &cv; }
+      if (res->over_scenario) {
+        rc.over_scenario = res->over_scenario + ow; rc.over_branch = res->over_branch + ow; rc.over_capacity = res->over_capacity - ow; rc.over_count = &co;
+        rc.over_loading_pct = res->over_loading_pct ? res->over_loading_pct + ow : nullptr;
+      }
+      if (res->qlog_scenario) {
+        rc.qlog_scenario = res->qlog_scenario + qw; rc.qlog_iter = res->qlog_iter + qw; rc.qlog_bus = res->qlog_bus + qw; rc.qlog_side = res->qlog_side + qw;
+        rc.qlog_capacity = res->qlog_capacity - qw; rc.qlog_count = &cq;
+      }
+      cv = co = cq = 0;
+      solve_injections_chunk(h, b0, nb, s_spec, qload_pu, &rc);
+      vtot += cv; otot += co; qtot += cq;
+      vw = std::min<int64_t>(res->viol_capacity, vw + cv); ow = std::min<int64_t>(res->over_capacity, ow + co); qw = std::min<int64_t>(res->qlog_capacity, qw + cq);
+      const sblx_stats& st = h->stats;
+      acc.total_ms += st.total_ms; acc.factor_ms += st.factor_ms; acc.solve_ms += st.solve_ms; acc.mismatch_ms += st.mismatch_ms;
+      acc.jacobian_ms += st.jacobian_ms; acc.other_ms += st.other_ms; acc.h2d_ms += st.h2d_ms; acc.d2h_ms += st.d2h_ms;
+      acc.host_prep_ms += st.host_prep_ms; acc.launches += st.launches; acc.factor_launches += st.factor_launches; acc.ticks += st.ticks;
+      acc.scenario_iterations += st.scenario_iterations; acc.mismatch_evaluations += st.mismatch_evaluations;
+      acc.scenarios_solved += st.scenarios_solved; acc.h2d_bytes += st.h2d_bytes; acc.d2h_bytes += st.d2h_bytes;
+      acc.tiny_pivots += st.tiny_pivots; acc.refine_passes += st.refine_passes;
+    }
+    if (res->viol_count) *res->viol_count = vtot;
+    if (res->over_count) *res->over_count = otot;
+    if (res->qlog_count) *res->qlog_count = qtot;
+    acc.n_ranks = 1; acc.shard_hi = B;
+    h->stats = acc;
+  }
   API_END(h)
 }
 

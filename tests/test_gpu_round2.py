@@ -470,3 +470,34 @@ def test_iterative_refinement_path_keeps_parity(prearmed):
             assert np.max(np.abs(raw["V"][i] - o.V)) <= VTOL
             assert np.array_equal(raw["bus_type_final"][i], o.types.astype(np.uint8))
     assert np.array_equal(raw["iterations"], ref["iterations"]) and np.max(np.abs(raw["V"] - ref["V"])) <= 1e-10
+
+
+def test_explicit_injection_sweep_streams_in_chunks(monkeypatch):
+    """sblx_solve_injections streams the per-scenario injection matrices through the device in chunks of scenarios
+    (a large sweep never needs B x n resident); forced here with a tiny budget: rows, lists and statistics of the
+    chunked run equal the single-batch run."""
+    g = G.tiled_grid(rows=10, cols=10, augment=True, pv_every=3, pv_q_mvar=20.0, rating_mva=3.0)
+    eng, a, vm, va = _warm_engine(g, vm_min_pu=0.99, vm_max_pu=1.015)
+    rng = np.random.default_rng(99)
+    B = 100
+    f = np.clip(rng.normal(1.0, 0.15, size=(B, g.n)), 0.5, 1.5)
+    isload = a.s_spec.real < 0
+    S, ql = np.where(isload, a.s_spec * f, a.s_spec), np.where(isload, a.qload * f, a.qload)
+
+    def run():
+        r = eng._alloc(B, g.n, True, True, want_lists=True)
+        s = eng._results_struct(r)
+        api.L.check(eng.lib.sblx_solve_injections(eng.h, B, api.L.ptr(np.ascontiguousarray(S).view(np.float64), api.L.c_f64p),
+                                                  api.L.ptr(np.ascontiguousarray(ql), api.L.c_f64p), api.C.byref(s)), eng.h)
+        return eng._finish_lists(r), eng.stats()
+
+    one, st1 = run()
+    monkeypatch.setenv("SBLX_SWEEP_CHUNK_GB", "0.0001")          # 100 KB: 41 scenarios per chunk
+    many, st2 = run()
+    eng.close()
+    for k in ("converged", "iterations", "status", "V", "bus_type_final", "n_voltage_violations", "n_overloaded", "violations", "overloads",
+              "qlimit_events"):
+        assert np.array_equal(one[k], many[k]), k
+    assert len(one["overloads"]) > 0 and len(one["violations"]) > 0
+    assert st2["scenarios_solved"] == st1["scenarios_solved"] == B and st2["scenario_iterations"] == st1["scenario_iterations"]
+    assert st2["ticks"] > st1["ticks"]
