@@ -487,11 +487,14 @@ struct sblx_handle {
   cudaEvent_t stage_ev[2] = {};
   sblx_stats stats{};
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ring_ev[4] = {};     // look-ahead ticks of small batches: "counters of tick k are on the host"
 
   ~sblx_handle() {
     if (cuda_ready) {
       cudaSetDevice(device);
       for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+      for (auto& e : ring_ev)
         if (e) cudaEventDestroy(e);
       if (pinned_counts) cudaFreeHost(pinned_counts);
       for (int k = 0; k < 2; ++k) {
@@ -722,7 +725,8 @@ static void ensure_cuda(sblx_handle* h) {
   h->device = dev;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
-  CK(cudaMallocHost(&h->pinned_counts, 8 * sizeof(int)));
+  for (auto& ev : h->ring_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaMallocHost(&h->pinned_counts, 8 * 5 * sizeof(int)));    // [0..8): the synchronous loop, then 4 ring entries
   h->cuda_ready = true;
   upload_model(h);
 }
@@ -1244,6 +1248,90 @@ static void launch_factor(sblx_handle* h, int nstep) {
   }
 }
 
+// Small batches (everything resident from the first tick, at most 1024 scenarios): the per-tick host round trip and the
+// launch latency of ~20 tiny kernels dominate (IEEE-14 N-1: 31 ticks).  Every kernel sizes its own work from the device
+// counters and exits early beyond them, so a tick can be enqueued from an UPPER BOUND of the running scenarios alone; the
+// host therefore stays two ticks ahead of the device and consumes the counters of tick k while ticks k+1, k+2 run.  Cost:
+// at most two empty ticks after the last scenario finished.  Falls back to the synchronous loop (returns with the state in
+// running / qhead) as soon as a tiny pivot was seen, because the refinement pass needs a round trip of its own.
+// Per-phase timings are not taken here (total_ms is).
+static void run_lookahead_prefix(sblx_handle* h, int64_t& running, int64_t& qhead, bool& saw_tiny) {
+  cudaStream_t s = h->stream;
+  const HostModel& H = h->H;
+  const int n = H.n, m = H.m, nnzB = (int)H.jb_col.size();
+  sblx_stats& st = h->stats;
+  const int64_t nq = h->nq;
+  constexpr int R = 4, D = 2;
+  const int maxticks = h->opt.max_iter + 4;
+  int ub = (int)nq, enq = 0, consumed = 0;
+  bool stop = false;
+  auto enqueue_tick = [&](int assign, int ubound) {
+    const int u = std::max(ubound, 1);
+    k_assign<<<1, 1024, 0, s>>>(h->M, h->A, h->L, h->Bt);
+    st.launches++;
+    if (assign > 0) {
+      k_init<<<dim3((n + 7) / 8, (unsigned)((assign + 31) / 32)), dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
+      k_init_iso<<<(unsigned)((assign + 127) / 128), 128, 0, s>>>(h->M, h->A, h->L, h->Bt);
+      st.launches += 2;
+    }
+    const dim3 gb((n + 7) / 8, (unsigned)((u + 31) / 32));
+    k_mismatch<<<gb, dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+    st.launches++;
+    if (h->opt.qlimits_enabled) {
+      k_qlimit<<<gb, dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
+      k_norm<<<u, 256, 0, s>>>(h->M, h->A, h->L);
+      st.launches += 2;
+    }
+    k_decide<<<1, 1024, 0, s>>>(h->M, h->A, h->L);
+    k_jacobian<<<dim3((nnzB + 31) / 32, (u + 31) / 32), dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+    st.launches += 2;
+    launch_factor(h, u);
+    for (int l = (int)h->solve_groups.size() - 1; l >= 0; --l)
+      for (const LaunchGroup& g : h->solve_groups[l]) {
+        launch_solve_group(h, g, u);
+        st.launches++;
+      }
+    if (h->M.pivot_tol > 0.0) {
+      k_tiny_guard<<<u, 256, 0, s>>>(h->M, h->A, h->L);
+      st.launches++;
+    }
+    k_update<<<dim3((m + 7) / 8, (u + 31) / 32), dim3(32, 8), 0, s>>>(h->M, h->A, h->L);
+    k_poststep<<<(u + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L);
+    k_fin_init<<<(u + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L);
+    k_fin_bus<<<gb, dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
+    if (H.nbr > 0) {
+      k_fin_branch<<<dim3((H.nbr + 7) / 8, (u + 31) / 32), dim3(32, 8), 0, s>>>(h->M, h->A, h->L, h->Bt);
+      st.launches++;
+    }
+    k_fin_write<<<(u + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L, h->Bt);
+    st.launches += 5;
+  };
+  for (;;) {
+    while (!stop && enq - consumed <= D && enq < maxticks) {
+      enqueue_tick(enq == 0 ? (int)nq : 0, ub);
+      CK(cudaMemcpyAsync(h->pinned_counts + 8 * (1 + enq % R), h->l_counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaEventRecord(h->ring_ev[enq % R], s));
+      ++enq;
+    }
+    if (consumed == enq) break;
+    CK(cudaEventSynchronize(h->ring_ev[consumed % R]));
+    const int* c = h->pinned_counts + 8 * (1 + consumed % R);
+    ++consumed;
+    const int nactive = c[0], nstep = c[2], nfin = c[3], ndrain = c[5];
+    if (nactive + ndrain > 0) {
+      st.ticks++;
+      st.mismatch_evaluations += nactive;
+      st.scenario_iterations += nstep;
+    }
+    qhead = c[4];
+    running = (int64_t)nactive + ndrain - nfin;
+    ub = std::min<int>(ub, (int)running);
+    if (c[7] > 0) { saw_tiny = true; stop = true; }                    // drain what is in flight, then the synchronous loop takes over
+    if (running == 0 && qhead >= nq) stop = true;
+  }
+  CK(cudaGetLastError());
+}
+
 static void run_staged(sblx_handle* h) {
   if (!h->staged) throw std::invalid_argument("sblx_run_staged: nothing staged");
   ensure_cuda(h);
@@ -1268,6 +1356,8 @@ static void run_staged(sblx_handle* h) {
   // SBLX_PROFILE_TICK=k brackets tick k (1-based) of this run with cudaProfilerStart/Stop (ncu --profile-from-start off)
   const char* ptick_env = getenv("SBLX_PROFILE_TICK");
   const long ptick = (ptick_env && nq > 1) ? atol(ptick_env) : 0;
+  if (nq <= std::min<int64_t>(W, 1024) && h->opt.factor_mode != 1 && ptick == 0 && (h->M.pf_mode & 3072) == 0 && !getenv("SBLX_NO_LOOKAHEAD"))
+    run_lookahead_prefix(h, running, qhead, tiny_mode);
   while (running > 0 || qhead < nq) {
     if (ptick > 0 && st.ticks + 1 == ptick) cudaProfilerStart();
     const int64_t assign = std::min<int64_t>(W - running, nq - qhead);
