@@ -1307,7 +1307,9 @@ static void run_lookahead_prefix(sblx_handle* h, int64_t& running, int64_t& qhea
     st.launches += 5;
   };
   for (;;) {
-    while (!stop && enq - consumed <= D && enq < maxticks) {
+    // the first ticks are taken one at a time (most scenarios are done after four or five iterations: running ahead
+    // would only add empty ticks); the look-ahead pays on the tail of stragglers that iterate on
+    while (!stop && enq - consumed <= (consumed >= 4 ? D : 0) && enq < maxticks) {
       enqueue_tick(enq == 0 ? (int)nq : 0, ub);
       CK(cudaMemcpyAsync(h->pinned_counts + 8 * (1 + enq % R), h->l_counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CK(cudaEventRecord(h->ring_ev[enq % R], s));
