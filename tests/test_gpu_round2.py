@@ -501,3 +501,19 @@ def test_explicit_injection_sweep_streams_in_chunks(monkeypatch):
     assert len(one["overloads"]) > 0 and len(one["violations"]) > 0
     assert st2["scenarios_solved"] == st1["scenarios_solved"] == B and st2["scenario_iterations"] == st1["scenario_iterations"]
     assert st2["ticks"] > st1["ticks"]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+def test_multi_engine_with_fewer_scenarios_than_gpus_and_repeated_calls():
+    """a rank without scenarios only takes part in the gather; handles are reusable across batch sizes"""
+    g = G.case14()
+    eng, a, vm, va = _warm_engine(g)
+    cases = O.generate_n1_branches(g)
+    ref = eng.solve_outages(cases, want_lists=True)
+    eng.close()
+    me = api.MultiEngine(a, 2)
+    for sel in ([3], [0, 1, 2], list(range(len(cases))), [5]):
+        r = me.solve_outages([cases[i] for i in sel], want_lists=True)
+        for k in ("converged", "status", "iterations", "V", "bus_type_final", "island_count", "n_switch_events"):
+            assert np.array_equal(r[k], ref[k][sel]), (k, sel)
+    me.close()
