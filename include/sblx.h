@@ -302,6 +302,18 @@ int sblx_multi_solve_outages(sblx_multi* m, int64_t B, const int32_t* outage_ptr
 int sblx_multi_get_stats(const sblx_multi* m, int32_t dev_index, sblx_stats* stats);
 sblx_handle* sblx_multi_handle(sblx_multi* m, int32_t dev_index); /* borrowed: e.g. sblx_solve_one on device 0 */
 
+/* ---- MATPOWER `.m` case reader (host only; text rules of src/MatpowerIO.jl:268-514) -----------------------------------
+ * baseMVA and the bus / gen / branch matrices padded or truncated to the MATPOWER v2 widths 13 / 21 / 13 (row-major),
+ * `%` comments stripped, rows split at `;` / CR / LF, bus rows sorted by BUS_I when they are not, raw TAP kept (0 = line).
+ * Errors: SBLX_E_ARG with the text in sblx_mpc_last_error(). */
+typedef struct sblx_mpc sblx_mpc; /* opaque */
+int sblx_mpc_read(const char* path, sblx_mpc** out);
+int sblx_mpc_parse(const char* text, sblx_mpc** out);
+int sblx_mpc_dims(const sblx_mpc* m, double* base_mva, int64_t* nbus, int64_t* ngen, int64_t* nbranch);
+int sblx_mpc_tables(const sblx_mpc* m, double* bus /* [nbus*13] */, double* gen /* [ngen*21] */, double* branch /* [nbranch*13] */);
+void sblx_mpc_free(sblx_mpc* m);
+const char* sblx_mpc_last_error(void);
+
 /* ---- test / parity hooks (one scenario, every intermediate exposed) ---------------------- */
 /* Block pattern of the Jacobian: CSR over the m = n-1 non-slack buses in ascending bus order;
  * col entries are bus indices (0-based). */

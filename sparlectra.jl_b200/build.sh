@@ -5,5 +5,5 @@ cd "$(dirname "$0")/csrc"
 mkdir -p ../lib
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3 -shared \
-  engine.cu symbolic.cpp -o ../lib/libsblx.so "$@"
+  engine.cu symbolic.cpp matpower.cpp -o ../lib/libsblx.so "$@"
 echo "built $(cd ../lib && pwd)/libsblx.so"

@@ -73,6 +73,7 @@ EXPORTS = [
     "sblx_comm_unique_id", "sblx_comm_init_rank", "sblx_comm_destroy", "sblx_solve_outages_sharded", "sblx_shard_bounds",
     "sblx_create_multi", "sblx_destroy_multi", "sblx_multi_last_error", "sblx_multi_set_v0", "sblx_multi_set_locked_pv",
     "sblx_multi_solve_outages", "sblx_multi_get_stats", "sblx_multi_handle", "sblx_debug_set_pf_mode",
+    "sblx_mpc_read", "sblx_mpc_parse", "sblx_mpc_dims", "sblx_mpc_tables", "sblx_mpc_free", "sblx_mpc_last_error",
 ]
 
 _lib = None
@@ -136,6 +137,14 @@ def load():
     lib.sblx_multi_handle.argtypes = [vp, C.c_int32]
     lib.sblx_multi_handle.restype = vp
     lib.sblx_debug_set_pf_mode.argtypes = [vp, C.c_int32]
+    lib.sblx_mpc_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.sblx_mpc_parse.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.sblx_mpc_dims.argtypes = [vp, c_f64p, c_i64p, c_i64p, c_i64p]
+    lib.sblx_mpc_tables.argtypes = [vp, c_f64p, c_f64p, c_f64p]
+    lib.sblx_mpc_free.argtypes = [vp]
+    lib.sblx_mpc_free.restype = None
+    lib.sblx_mpc_last_error.argtypes = []
+    lib.sblx_mpc_last_error.restype = C.c_char_p
     for name in EXPORTS:
         if getattr(lib, name).restype is C.c_int and name not in ("sblx_version",):
             getattr(lib, name).restype = C.c_int

@@ -81,3 +81,29 @@ def read_case_m(path_or_text: str, legacy_compat: bool = True) -> dict:
 def grid_from_case(path_or_text: str) -> G.Grid:
     c = read_case_m(path_or_text)
     return G.from_matpower_tables(c["name"], c["baseMVA"], c["bus"], c["gen"], c["branch"])
+
+
+def read_case_m_native(path_or_text: str) -> dict:
+    """The same tables through the library's C reader (sblx_mpc_read / sblx_mpc_parse, csrc/matpower.cpp)."""
+    import ctypes as C
+    from . import lib as L
+    lib = L.load()
+    h = C.c_void_p()
+    if "\n" not in path_or_text and os.path.exists(path_or_text):
+        name = os.path.splitext(os.path.basename(path_or_text))[0]
+        rc = lib.sblx_mpc_read(path_or_text.encode(), C.byref(h))
+    else:
+        m = re.search(r"function\s+mpc\s*=\s*(\w+)", path_or_text)
+        name = m.group(1) if m else "case"
+        rc = lib.sblx_mpc_parse(path_or_text.encode(), C.byref(h))
+    if rc != 0:
+        raise ValueError(lib.sblx_mpc_last_error().decode())
+    try:
+        base = C.c_double()
+        nb, ng, nl = C.c_int64(), C.c_int64(), C.c_int64()
+        lib.sblx_mpc_dims(h, C.byref(base), C.byref(nb), C.byref(ng), C.byref(nl))
+        bus, gen, br = np.zeros((nb.value, 13)), np.zeros((ng.value, 21)), np.zeros((nl.value, 13))
+        lib.sblx_mpc_tables(h, L.ptr(bus, L.c_f64p), L.ptr(gen, L.c_f64p), L.ptr(br, L.c_f64p))
+    finally:
+        lib.sblx_mpc_free(h)
+    return {"name": name, "baseMVA": base.value, "bus": bus, "gen": gen, "branch": br}

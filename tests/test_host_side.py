@@ -390,3 +390,29 @@ def test_julia_struct_layouts_follow_the_header():
     assert [f for f, _ in L.Results._fields_] == c_fields("sblx_results")
     assert [f for f, _ in L.Stats._fields_] == c_fields("sblx_stats")
     assert [f for f, _ in L.Info._fields_] == c_fields("sblx_info")
+
+
+def test_native_matpower_reader_equals_the_python_reader():
+    """sblx_mpc_read / sblx_mpc_parse (csrc/matpower.cpp, the C reader behind the ABI) against the Python
+    reader on the committed IEEE-14 case file and on the text-rule fixture (comments, mixed row separators, unsorted bus
+    rows, short and long rows); same error behaviour."""
+    from sblx import matpower as MP
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "golden", "case14.m")
+    a, b = MP.read_case_m(path), MP.read_case_m_native(path)
+    assert a["name"] == b["name"] and a["baseMVA"] == b["baseMVA"]
+    for k in ("bus", "gen", "branch"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    txt = ("function mpc = tiny\n% header ; with [ brackets ]; inside a comment\nmpc.baseMVA = 50.5;\n"
+           "mpc.bus = [ 3 1 10 5 0 0 1 1.0 0 110 1 1.1 0.9   % unsorted, newline-separated rows (RTS-GMLC style)\n"
+           "  1 3 0 0 0 0 1 1.02 0 110 1 1.1 0.9\n\n  2 2 0 0 0 0 1 1.01 0 110 1 1.1 0.9 99 98 ];\n"
+           "mpc.gen = [1 50 0 100 -100 1.02 100 1 150 0; 2 25 0 80 -80 1.01 100 1 100 0;];\n"
+           "mpc.branch = [1 2 0.02 0.08 0.02 999 999 999 0 0 1;\r\n 2 3 0.02 0.08 0.02 0 0 0 0 0 1; 1 3 0.03 0.1 0 0 0 0 1.0 5 1 -360 360 7];\n")
+    a, b = MP.read_case_m(txt), MP.read_case_m_native(txt)
+    assert b["name"] == "tiny" and b["baseMVA"] == 50.5
+    for k in ("bus", "gen", "branch"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    with pytest.raises(ValueError, match="baseMVA"):
+        MP.read_case_m_native("mpc.bus = [1 2 3];\n")
+    with pytest.raises(ValueError, match="mpc.gen"):
+        MP.read_case_m_native("mpc.baseMVA = 100;\nmpc.bus = [1 3 0 0 0 0 1 1 0 1 1 1 1];\n")

@@ -1,6 +1,6 @@
 """Per-phase cycle breakdown of k_front (thread 0's view) by size class.  Needs the instrumented build:
   (cd sparlectra.jl_b200/csrc && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
-     -Xcompiler -fPIC,-O3 -shared -DSBLX_PHASE_TIMING engine.cu symbolic.cpp -o ../lib/libsblx_timing.so)
+     -Xcompiler -fPIC,-O3 -shared -DSBLX_PHASE_TIMING engine.cu symbolic.cpp matpower.cpp -o ../lib/libsblx_timing.so)
 The clock reads and atomics slow the kernels down (about 2x) and distort the chain phase: use it for the
 relative size of the other phases and trust tools/ncu_phases.py for stall attribution."""
 import sys, os, ctypes as C
