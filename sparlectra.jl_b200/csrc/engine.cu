@@ -1306,11 +1306,42 @@ static void run_lookahead_prefix(sblx_handle* h, int64_t& running, int64_t& qhea
     k_fin_write<<<(u + 127) / 128, 128, 0, s>>>(h->M, h->A, h->L, h->Bt);
     st.launches += 5;
   };
+  // In the look-ahead phase consecutive ticks are the same ~25 launches with the same grids as long as the upper bound
+  // does not move (a straggler iterating to the cap): the tick is captured into a CUDA graph once per bound and replayed
+  // with one cudaGraphLaunch instead of ~25 kernel launches.
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int graph_ub = -1;
+  int64_t graph_launches = 0, graph_factor_launches = 0;
+  const bool use_graph = getenv("SBLX_NO_GRAPH") == nullptr;
+  auto drop_graph = [&]() {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    gexec = nullptr; graph = nullptr; graph_ub = -1;
+  };
+  auto replay_tick = [&](int ubound) -> bool {
+    if (ubound != graph_ub) {
+      drop_graph();
+      const int64_t l0 = st.launches, f0 = st.factor_launches;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+      enqueue_tick(0, ubound);
+      const cudaError_t e1 = cudaStreamEndCapture(s, &graph);
+      graph_launches = st.launches - l0;
+      graph_factor_launches = st.factor_launches - f0;
+      st.launches = l0; st.factor_launches = f0;          // counted per replay below
+      if (e1 != cudaSuccess || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) { cudaGetLastError(); drop_graph(); return false; }
+      graph_ub = ubound;
+    }
+    if (cudaGraphLaunch(gexec, s) != cudaSuccess) { cudaGetLastError(); drop_graph(); return false; }
+    st.launches += graph_launches;
+    st.factor_launches += graph_factor_launches;
+    return true;
+  };
   for (;;) {
     // the first ticks are taken one at a time (most scenarios are done after four or five iterations: running ahead
     // would only add empty ticks); the look-ahead pays on the tail of stragglers that iterate on
     while (!stop && enq - consumed <= (consumed >= 4 ? D : 0) && enq < maxticks) {
-      enqueue_tick(enq == 0 ? (int)nq : 0, ub);
+      if (!(use_graph && consumed >= 4 && enq > 0 && replay_tick(ub))) enqueue_tick(enq == 0 ? (int)nq : 0, ub);
       CK(cudaMemcpyAsync(h->pinned_counts + 8 * (1 + enq % R), h->l_counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CK(cudaEventRecord(h->ring_ev[enq % R], s));
       ++enq;
@@ -1331,6 +1362,7 @@ static void run_lookahead_prefix(sblx_handle* h, int64_t& running, int64_t& qhea
     if (c[7] > 0) { saw_tiny = true; stop = true; }                    // drain what is in flight, then the synchronous loop takes over
     if (running == 0 && qhead >= nq) stop = true;
   }
+  drop_graph();
   CK(cudaGetLastError());
 }
 
