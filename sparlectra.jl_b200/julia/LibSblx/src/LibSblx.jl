@@ -214,4 +214,30 @@ function solve_outages(h::Handle, cases::Vector{Vector{Int}}; want_v::Bool = fal
   return BatchResults(conv, st, it, nsw, isl, fm, vmin, vmax, ld, nvv, nov, ntp, violations, overloads, V)
 end
 
+"""
+    solve_injection_sweep(h, B; first = 0, seed = 20260724, sigma = 0.1, lo = 0.5, hi = 1.5) -> BatchResults
+
+Monte-Carlo load sweep generated ON THE DEVICE (`sblx_solve_injection_sweep`): scenario s scales P and Q of every load bus
+by an independent truncated-normal factor from Philox4x32-10 keyed on (seed, first + s, bus) - the recipe of
+examples/powerflow/mc_probabilistic_powerflow.jl:28-41.  Single-GPU handles only; split a study over several handles /
+processes with `first` (the generator is counter based: a draw does not depend on batching).
+"""
+function solve_injection_sweep(h::Handle, B::Int; first::Int = 0, seed::Integer = 20260724, sigma::Float64 = 0.1, lo::Float64 = 0.5,
+                               hi::Float64 = 1.5)
+  h.multi && error("solve_injection_sweep: use one single-GPU handle per device and split the study with `first`")
+  z32() = zeros(Int32, B); zf() = zeros(Float64, B)
+  conv = zeros(UInt8, B); st = z32(); it = z32(); nsw = z32(); isl = z32(); fm = zf(); vmin = zf(); vmax = zf(); ld = zf()
+  nvv = z32(); nov = z32(); ntp = z32()
+  GC.@preserve conv st it nsw isl fm vmin vmax ld nvv nov ntp begin
+    res = Results(pointer(conv), pointer(st), pointer(it), pointer(nsw), pointer(isl), pointer(fm), pointer(vmin), pointer(vmax), pointer(ld),
+                  Ptr{Float64}(C_NULL), Ptr{UInt8}(C_NULL), pointer(nvv), pointer(nov), pointer(ntp),
+                  0, Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), Ptr{Int64}(C_NULL), 0, Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), Ptr{Float64}(C_NULL),
+                  Ptr{Int64}(C_NULL), 0, Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), Ptr{Int64}(C_NULL),
+                  Ptr{Float64}(C_NULL))
+    check(ccall((:sblx_solve_injection_sweep, libsblx), Cint, (Ptr{Cvoid}, Int64, Int64, UInt64, Float64, Float64, Float64, Ref{Results}),
+                h.ptr, B, first, UInt64(seed), sigma, lo, hi, res), h.ptr)
+  end
+  return BatchResults(conv, st, it, nsw, isl, fm, vmin, vmax, ld, nvv, nov, ntp, [Int[] for _ in 1:B], [Int[] for _ in 1:B], nothing)
+end
+
 end # module LibSblx

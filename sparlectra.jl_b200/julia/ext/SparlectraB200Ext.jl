@@ -171,4 +171,24 @@ function run_contingencies_batched!(net::Sparlectra.Net, cases::Vector{Sparlectr
   return out
 end
 
+"""
+    run_injection_sweep(net, n_draws; sigma = 0.1, lo = 0.5, hi = 1.5, seed = 20260724, maxIte = 30, tol = 1e-8, pf_kwargs...)
+
+The serial Monte-Carlo loop of examples/powerflow/mc_probabilistic_powerflow.jl:73-99 (draw load factors, `runpf!`, collect
+the voltage band and loading) as ONE device-side sweep: the base case is solved by the reference `runpf!`, every draw
+starts from it, the factors are generated on the GPU.  Returns the per-draw summary (`LibSblx.BatchResults`).
+"""
+function run_injection_sweep(net::Sparlectra.Net, n_draws::Int; sigma::Float64 = 0.1, lo::Float64 = 0.5, hi::Float64 = 1.5,
+                             seed::Integer = 20260724, maxIte::Int = 30, tol::Float64 = 1e-8, pf_kwargs...)
+  template = deepcopy(net)
+  _, erg = Sparlectra.runpf!(template, maxIte, tol, 0; islands_enabled = true, pf_kwargs...)
+  erg == 0 || error("run_injection_sweep: the base case did not converge")
+  eng = engine_from_net(template; tol = tol, maxIte = maxIte, pf_kwargs...)
+  try
+    return LibSblx.solve_injection_sweep(eng, n_draws; seed = seed, sigma = sigma, lo = lo, hi = hi)
+  finally
+    LibSblx.destroy!(eng)
+  end
+end
+
 end # module SparlectraB200Ext
